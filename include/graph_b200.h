@@ -1,0 +1,225 @@
+/*
+ * graph_b200.h — C ABI of libgraph_b200.so
+ *
+ * The drop-in boundary for the CSR hot path of neo4j-labs/graph (crate `graph`,
+ * crates/algos + crates/builder).  The reference has no FFI of its own: its
+ * seams are the generic functions in crates/algos/src/{page_rank,wcc,sssp,
+ * triangle_count}.rs over the CSR types of crates/builder/src/graph/csr.rs.
+ * Each entry point below names the reference item (file:line, relative to the
+ * reference checkout) it replaces; INTEGRATION.md shows the `extern "C"` block
+ * a maintainer adds on the Rust side.
+ *
+ * Conventions
+ *   - node ids and CSR offsets are uint32_t (the reference's NI = u32:
+ *     csr.rs:124 `Csr<NI, NI, EV>` uses NI for offsets too), so m < 2^32.
+ *   - every pointer argument is a HOST pointer unless its name starts with
+ *     `d_` (device pointer on the graph's device).
+ *   - all calls return gb_status; on failure gb_last_error() holds a
+ *     thread-local message.  Nothing unwinds or aborts across the ABI.
+ *   - a gb_graph is immutable after creation except gb_make_degree_ordered
+ *     (exclusive access, like `&mut self` in graph_ops.rs:173).
+ *   - there is NO CPU fallback: if no CUDA device is usable every graph
+ *     constructor fails with GB_ERR_CUDA.
+ */
+#ifndef GRAPH_B200_H
+#define GRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_ABI_VERSION 1
+
+typedef enum gb_status {
+  GB_OK = 0,
+  GB_ERR_INVALID = 1,     /* bad argument (null pointer, id out of range, n == 0, ...) */
+  GB_ERR_CUDA = 2,        /* CUDA runtime error / no device */
+  GB_ERR_OOM = 3,         /* device or host allocation failed */
+  GB_ERR_UNSUPPORTED = 4  /* wrong graph kind for the call (e.g. TC on a directed graph) */
+} gb_status;
+
+/* crates/builder/src/graph/csr.rs:35-45  `enum CsrLayout` */
+typedef enum gb_layout {
+  GB_LAYOUT_UNSORTED = 0,     /* default; here: deterministic edge-list order */
+  GB_LAYOUT_SORTED = 1,       /* rows ascending, duplicates kept (csr.rs:886-895) */
+  GB_LAYOUT_DEDUPLICATED = 2  /* sorted, unique, self-loops removed (csr.rs:897-948) */
+} gb_layout;
+
+typedef enum gb_graph_kind {
+  GB_KIND_DIRECTED = 0,   /* DirectedCsrGraph<u32>   csr.rs:364-368 */
+  GB_KIND_UNDIRECTED = 1  /* UndirectedCsrGraph<u32> csr.rs:658-661 */
+} gb_graph_kind;
+
+/* which CSR of a graph an accessor refers to */
+typedef enum gb_csr_which {
+  GB_CSR_OUT = 0,        /* csr_out  (directed)  */
+  GB_CSR_IN = 1,         /* csr_inc  (directed)  */
+  GB_CSR_UNDIRECTED = 2  /* csr      (undirected)*/
+} gb_csr_which;
+
+/* opaque device-resident twin of DirectedCsrGraph / UndirectedCsrGraph */
+typedef struct gb_graph gb_graph;
+
+typedef struct gb_graph_info {
+  uint32_t kind;          /* gb_graph_kind */
+  uint32_t node_count;    /* Graph::node_count  lib.rs:315-321 */
+  uint64_t edge_count;    /* Graph::edge_count: directed = |out targets|; undirected = |targets|/2 (csr.rs:687-689) */
+  uint64_t target_count;  /* entries in the out (or undirected) targets array */
+  uint32_t has_weights;   /* 1 if the out-CSR carries f32 edge values (Target<u32,f32>, graph/mod.rs:6-10) */
+  int32_t device;         /* CUDA device ordinal the arrays live on */
+  uint64_t device_bytes;  /* HBM held by this handle */
+} gb_graph_info;
+
+/* crates/algos/src/page_rank.rs:14-56  `PageRankConfig` (+ a schedule selector) */
+typedef enum gb_pr_mode {
+  GB_PR_AUTO = 0,    /* n <= 16384 -> GB_PR_EXACT, else GB_PR_JACOBI */
+  GB_PR_EXACT = 1,   /* the reference's sweep as ONE thread runs it: in place, CSR-order f32 sums
+                        (page_rank.rs:142-160). Bit-exact with the reference whenever the reference
+                        itself is deterministic (n <= CHUNK_SIZE = 16384, page_rank.rs:12). Sequential. */
+  GB_PR_JACOBI = 2   /* throughput path: double-buffered sweep (every read sees iteration k), deterministic */
+} gb_pr_mode;
+
+typedef struct gb_page_rank_config {
+  uint64_t max_iterations; /* DEFAULT_MAX_ITERATIONS = 20   page_rank.rs:46 */
+  double tolerance;        /* DEFAULT_TOLERANCE = 1e-4      page_rank.rs:47 */
+  float damping_factor;    /* DEFAULT_DAMPING_FACTOR = 0.85 page_rank.rs:48 */
+  uint32_t mode;           /* gb_pr_mode */
+} gb_page_rank_config;
+
+/* crates/algos/src/wcc.rs:40-79  `WccConfig` */
+typedef struct gb_wcc_config {
+  uint64_t chunk_size;      /* 16384 — scheduling only in the reference; ignored on device */
+  uint64_t neighbor_rounds; /* 2 */
+  uint64_t sampling_size;   /* 1024 */
+} gb_wcc_config;
+
+/* crates/algos/src/sssp.rs:18-36  `DeltaSteppingConfig` */
+typedef struct gb_sssp_config {
+  uint64_t start_node;
+  float delta;
+} gb_sssp_config;
+
+/* per-call device timing of the last algorithm run on a graph (for bench / result `micros`) */
+typedef struct gb_timing {
+  double total_ms;       /* CUDA-event time of the whole device section of the call */
+  double hot_kernel_ms;  /* summed CUDA-event time of the dominant kernel (only when profiling is on) */
+  uint64_t hot_kernel_launches;
+  uint64_t kernel_launches; /* all kernels this library launched in the call */
+} gb_timing;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int gb_abi_version(void);
+const char* gb_last_error(void);
+/* number of usable CUDA devices (0 when none: every constructor then fails) */
+int gb_device_count(void);
+/* when on, algorithm calls bracket each launch of their dominant kernel with CUDA events */
+void gb_set_profiling(int on);
+
+/* ---- graph lifecycle ----------------------------------------------------------------------- */
+/* From already-built host CSR arrays: the device twin of an existing DirectedCsrGraph
+ * (csr.rs:364-368: csr_out + csr_inc).  out_w may be NULL (EV = ()).  Arrays are copied. */
+gb_status gb_digraph_from_csr_u32(int device, uint32_t node_count,
+                                  const uint32_t* out_offsets, const uint32_t* out_targets,
+                                  const float* out_weights,
+                                  const uint32_t* in_offsets, const uint32_t* in_targets,
+                                  gb_graph** graph);
+/* Device twin of an UndirectedCsrGraph (csr.rs:658-661); `targets` has offsets[n] entries. */
+gb_status gb_graph_from_csr_u32(int device, uint32_t node_count, const uint32_t* offsets,
+                                const uint32_t* targets, gb_graph** graph);
+
+/* From an edge list — replaces `Csr::from((&edges, node_count, direction, layout))`
+ * (csr.rs:124-221) and the DirectedCsrGraph/UndirectedCsrGraph `From<(E, CsrLayout)>` impls
+ * (csr.rs:522-543, :727-760): the CSR is built ON DEVICE (histogram, scan, radix sort).
+ * node_count == 0 means max id + 1 (edgelist.rs:84-90).  weights may be NULL.
+ * UNSORTED yields the single-thread order of the reference (edge-list order; for undirected
+ * graphs the outgoing pass first, then the incoming pass: csr.rs:154-172, :1199-1205). */
+gb_status gb_digraph_from_edges_u32(int device, const uint32_t* src, const uint32_t* dst,
+                                    const float* weights, uint64_t edge_count,
+                                    uint32_t node_count, gb_layout layout, gb_graph** graph);
+gb_status gb_graph_from_edges_u32(int device, const uint32_t* src, const uint32_t* dst,
+                                  uint64_t edge_count, uint32_t node_count, gb_layout layout,
+                                  gb_graph** graph);
+
+/* Synthetic R-MAT / Graph500-style graph generated on device (a,b,c,d = .57,.19,.19,.05,
+ * n = 2^scale, m = edge_factor * n, ids scrambled, duplicates and self-loops kept); the same
+ * generator exists on the CPU in oracle/ for parity.  The reference reads such inputs from a
+ * packed Graph500 file (input/graph500.rs:63-127, node_count = edge_count/16).
+ * weights != 0 attaches deterministic uniform (0,1] f32 edge values (for SSSP). */
+gb_status gb_digraph_rmat(int device, uint32_t scale, uint32_t edge_factor, uint64_t seed,
+                          gb_layout layout, int weights, gb_graph** graph);
+gb_status gb_graph_rmat(int device, uint32_t scale, uint32_t edge_factor, uint64_t seed,
+                        gb_layout layout, gb_graph** graph);
+/* the raw generator: fills host arrays with edges [first, first+count) of that stream */
+gb_status gb_rmat_edges(int device, uint32_t scale, uint64_t seed, uint64_t first, uint64_t count,
+                        uint32_t* src, uint32_t* dst);
+
+gb_status gb_graph_free(gb_graph* graph);
+gb_status gb_graph_get_info(const gb_graph* graph, gb_graph_info* info);
+/* copy a CSR back to the host (neighbour views of the host mirror: csr.rs:97-117).
+ * offsets: node_count+1 entries; targets: target_count entries; weights may be NULL. */
+gb_status gb_graph_copy_csr(const gb_graph* graph, gb_csr_which which, uint32_t* offsets,
+                            uint32_t* targets, float* weights);
+/* number of entries in the chosen CSR's targets array */
+gb_status gb_graph_csr_len(const gb_graph* graph, gb_csr_which which, uint64_t* len);
+/* the CUDA stream (cudaStream_t) all work of this graph is issued on */
+void* gb_graph_stream(const gb_graph* graph);
+gb_status gb_graph_last_timing(const gb_graph* graph, gb_timing* timing);
+
+/* ---- graph ops ----------------------------------------------------------------------------- */
+/* ToUndirectedOp::to_undirected (graph_ops.rs:229, csr.rs:391-464) */
+gb_status gb_to_undirected(const gb_graph* digraph, gb_layout layout, gb_graph** graph);
+/* RelabelByDegreeOp::make_degree_ordered (graph_ops.rs:173,250-252,511-638): new id = rank in
+ * (degree, old id) DESCENDING; rows rewritten and re-sorted.  Undirected graphs only. */
+gb_status gb_make_degree_ordered(gb_graph* graph);
+
+/* ---- algorithms ---------------------------------------------------------------------------- */
+/* page_rank(&graph, config) -> (Vec<f32>, usize, f64)     page_rank.rs:58-111
+ * scores: node_count floats, caller-owned. */
+gb_status gb_page_rank(const gb_graph* graph, const gb_page_rank_config* config, float* scores,
+                       uint64_t* ran_iterations, double* error);
+/* same, result left in HBM (d_scores: node_count floats on the graph's device) */
+gb_status gb_page_rank_device(const gb_graph* graph, const gb_page_rank_config* config,
+                              float* d_scores, uint64_t* ran_iterations, double* error);
+
+/* wcc_afforest(&graph, config).to_vec()                    wcc.rs:127-139, afforest.rs:100-114
+ * components[v] = root of v = minimum node id of v's weakly connected component. */
+gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* components);
+gb_status gb_wcc_device(const gb_graph* graph, const gb_wcc_config* config, uint32_t* d_components);
+
+/* delta_stepping(&graph, config) -> Vec<AtomicF32>          sssp.rs:38-102
+ * distances: node_count floats; unreachable = FLT_MAX (sssp.rs:12). */
+gb_status gb_sssp(const gb_graph* graph, const gb_sssp_config* config, float* distances);
+gb_status gb_sssp_device(const gb_graph* graph, const gb_sssp_config* config, float* d_distances);
+
+/* global_triangle_count(&graph) -> u64                      triangle_count.rs:22-86 */
+gb_status gb_triangle_count(const gb_graph* graph, uint64_t* triangles);
+
+/* ---- multi-GPU PageRank shard (1-D edge-cut by destination range) ---------------------------
+ * One process per GPU.  Rank p owns destination rows [row_begin,row_end) chosen by the
+ * reference's in_degree_partition rule (graph_ops.rs:431-439, :479-509).  The caller (torch
+ * distributed / NCCL) owns the exchange of the out_scores vector between steps. */
+typedef struct gb_pr_shard gb_pr_shard;
+
+/* ranges[0..parts] (parts+1 entries) for the graph's in-degree sequence */
+gb_status gb_in_degree_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
+/* builds the shard state for rows [row_begin,row_end) of `graph`'s in-CSR */
+gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t row_begin, uint32_t row_end,
+                             gb_pr_shard** shard);
+/* one Jacobi sweep over the shard's rows: reads the full d_x_cur[n], writes
+ * d_x_next[row_begin..row_end) (pointer to the FULL next vector) and, when peers != NULL, also
+ * stores the same slice into each d_peer_x_next[i] (peer-mapped full vectors: fused allgather).
+ * d_scores_local: row_end-row_begin floats. d_error: one double, overwritten. */
+gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x_cur,
+                           float* d_scores_local);
+gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, const float* d_x_cur,
+                           float* d_x_next, float* const* d_peer_x_next, uint32_t peer_count,
+                           float* d_scores_local, double* d_error, void* cuda_stream);
+gb_status gb_pr_shard_free(gb_pr_shard* shard);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPH_B200_H */
