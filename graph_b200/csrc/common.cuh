@@ -1,0 +1,140 @@
+// common.cuh — shared plumbing of libgraph_b200.so (error handling, device buffers, graph handle).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/graph_b200.h"
+
+namespace gb {
+
+// ---- thread-local error message behind gb_last_error() ---------------------------------------
+std::string& last_error();
+gb_status fail(gb_status st, const char* fmt, ...);
+
+#define GB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      gb_status _s = (_e == cudaErrorMemoryAllocation) ? GB_ERR_OOM : GB_ERR_CUDA;             \
+      return gb::fail(_s, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    }                                                                                          \
+  } while (0)
+
+#define GB_TRY(expr)                 \
+  do {                               \
+    gb_status _s = (expr);           \
+    if (_s != GB_OK) return _s;      \
+  } while (0)
+
+#define GB_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return gb::fail(GB_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+// ---- device buffer (RAII, cudaMallocAsync-free: plain cudaMalloc keeps ncu traces simple) -----
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  // allocates count elements (+ pad elements of slack so 128-bit loads may overrun the tail)
+  gb_status alloc(size_t count, size_t pad = 0) {
+    release();
+    size_t bytes = (count + pad) * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(e == cudaErrorMemoryAllocation ? GB_ERR_OOM : GB_ERR_CUDA,
+                  "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    n = count;
+    return GB_OK;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- device CSR ----------------------------------------------------------------------------
+// offsets[n+1] u32, targets[len] u32 (+8 entries of zeroed slack for 128-bit loads), optional
+// SoA weights[len] f32 (the host API exposes the reference's 8-byte AoS Target{u32,f32}).
+struct DevCsr {
+  DevBuf<uint32_t> off;
+  DevBuf<uint32_t> tgt;
+  DevBuf<float> w;
+  uint64_t len = 0;
+  bool present() const { return off.p != nullptr; }
+  uint64_t bytes() const { return off.bytes() + tgt.bytes() + w.bytes(); }
+};
+
+struct PrPlan;  // pagerank.cu
+
+}  // namespace gb
+
+// the opaque handle of the C ABI
+struct gb_graph {
+  int device = 0;
+  gb_graph_kind kind = GB_KIND_DIRECTED;
+  uint32_t n = 0;
+  gb::DevCsr out;  // directed: csr_out; undirected: the single csr
+  gb::DevCsr in;   // directed only: csr_inc
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  mutable std::mutex mu;            // algorithms on one handle serialise on its stream
+  mutable gb::PrPlan* pr_plan = nullptr;  // lazily built PageRank layout (pagerank.cu)
+  mutable gb_timing timing{};
+  uint64_t extra_bytes = 0;
+};
+
+namespace gb {
+void free_pr_plan(PrPlan* p);
+uint64_t pr_plan_bytes(const PrPlan* p);
+bool profiling_on();
+
+// RAII: make the graph's device current for the duration of a call
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// CSR construction on device (graph.cu)
+// rows/cols: device arrays of `count` entries (consumed / overwritten). Builds `csr` with the
+// given layout; n rows.  w may be null.
+gb_status build_csr_device(cudaStream_t s, uint32_t n, uint32_t* d_rows, uint32_t* d_cols, float* d_w,
+                           uint64_t count, gb_layout layout, DevCsr* csr);
+gb_status new_graph(int device, gb_graph_kind kind, uint32_t n, gb_graph** out);
+
+inline unsigned grid_for(uint64_t items, unsigned block, unsigned max_blocks = 148u * 16u) {
+  uint64_t b = (items + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<unsigned>(b);
+}
+}  // namespace gb

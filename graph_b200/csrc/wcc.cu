@@ -1,0 +1,176 @@
+// wcc.cu — weakly connected components (Afforest) on the device CSR pair.
+//
+// Replaces crates/algos/src/wcc.rs:127-139,158-301 (`wcc_afforest`, `sample_subgraph`,
+// `find_largest_component`, `link_remaining`) and crates/algos/src/afforest.rs:22-56,100-114
+// (`Afforest::union/compress/to_vec`).  Same five phases, same link rule (hook the higher root
+// under the lower with a CAS), so parent[x] <= x holds throughout and after the final compress
+// every entry is the minimum node id of its component — the value `to_vec()` returns.
+//
+// Algorithmic bytes per run: 8m + 16n + 8 (both CSRs once, parent read + write); the sampling
+// phase lets most vertices skip their edge lists, so effective GB/s can exceed the HBM peak.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gb {
+
+__device__ __forceinline__ uint32_t ld_parent(const uint32_t* p, uint32_t i) {
+  return *((const volatile uint32_t*)(p + i));
+}
+
+// Afforest::union, afforest.rs:22-39
+__device__ __forceinline__ void af_link(uint32_t* parent, uint32_t u, uint32_t v) {
+  uint32_t p1 = ld_parent(parent, u);
+  uint32_t p2 = ld_parent(parent, v);
+  while (p1 != p2) {
+    const uint32_t high = p1 > p2 ? p1 : p2;
+    const uint32_t low = p1 + p2 - high;
+    const uint32_t p_high = ld_parent(parent, high);
+    if (p_high == low) break;
+    if (p_high == high && atomicCAS(parent + high, high, low) == high) break;
+    p1 = ld_parent(parent, ld_parent(parent, high));
+    p2 = ld_parent(parent, low);
+  }
+}
+
+__global__ void k_cc_init(uint32_t* __restrict__ parent, uint32_t n) {
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) parent[v] = v;
+}
+
+// sample_subgraph, wcc.rs:186-204: link u with its first `rounds` out-neighbours
+__global__ void k_cc_sample(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t n,
+                            uint32_t round, uint32_t* parent) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const uint32_t b = off[u], e = off[u + 1];
+    if (b + round < e) af_link(parent, u, tgt[b + round]);
+  }
+}
+
+// Afforest::compress, afforest.rs:50-56
+__global__ void k_cc_compress(uint32_t* parent, uint32_t n) {
+  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+    uint32_t p = ld_parent(parent, x);
+    uint32_t pp = ld_parent(parent, p);
+    while (p != pp) {
+      parent[x] = pp;
+      p = pp;
+      pp = ld_parent(parent, p);
+    }
+  }
+}
+
+__global__ void k_cc_sample_labels(const uint32_t* __restrict__ parent, uint32_t n, uint32_t count,
+                                   uint64_t seed, uint32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = parent[(uint32_t)(z % n)];
+  }
+}
+
+// link_remaining, wcc.rs:274-301: one warp per vertex outside the sampled giant component
+__global__ void k_cc_link_remaining(const uint32_t* __restrict__ out_off, const uint32_t* __restrict__ out_tgt,
+                                    const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                                    uint32_t n, uint32_t rounds, uint32_t skip, int use_skip,
+                                    uint32_t* parent) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  // lanes first test 32 consecutive vertices, then the warp serves the survivors one by one
+  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t mine = base + lane;
+    bool live = mine < n;
+    if (live && use_skip) live = ld_parent(parent, mine) != skip;
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, live);
+    while (mask) {
+      const uint32_t u = base + (__ffs(mask) - 1);
+      mask &= mask - 1;
+      const uint32_t ob = out_off[u], oe = out_off[u + 1];
+      if (oe - ob > rounds)
+        for (uint32_t i = ob + rounds + lane; i < oe; i += 32) af_link(parent, u, out_tgt[i]);
+      const uint32_t ib = in_off[u], ie = in_off[u + 1];
+      for (uint32_t i = ib + lane; i < ie; i += 32) af_link(parent, u, in_tgt[i]);
+    }
+  }
+}
+
+static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t* d_comp, uint32_t* h_comp) {
+  GB_REQUIRE(g && cfg, "NULL argument");
+  if (g->kind != GB_KIND_DIRECTED)
+    return fail(GB_ERR_UNSUPPORTED, "wcc needs a directed graph (wcc.rs:130: DirectedNeighbors)");
+  DeviceGuard guard(g->device);
+  std::lock_guard<std::mutex> lock(g->mu);
+  cudaStream_t s = g->stream;
+  const uint32_t n = g->n;
+  DevBuf<uint32_t> tmp;
+  if (!d_comp) {
+    GB_TRY(tmp.alloc(n));
+    d_comp = tmp.p;
+  }
+  g->timing = gb_timing{};
+  GB_CUDA(cudaEventRecord(g->ev_begin, s));
+  const unsigned blk = 256;
+  const unsigned grid = grid_for(n, blk);
+  const uint32_t rounds = (uint32_t)std::min<uint64_t>(cfg->neighbor_rounds, 0xFFFFFFFFull);
+  k_cc_init<<<grid, blk, 0, s>>>(d_comp, n);
+  // `take(neighbor_rounds)` (wcc.rs:198) never looks past the row, so rounds beyond the largest
+  // out-degree are no-ops; cap the launch count accordingly
+  const uint32_t sample_rounds = std::min<uint32_t>(rounds, 64);
+  for (uint32_t r = 0; r < sample_rounds; ++r) k_cc_sample<<<grid, blk, 0, s>>>(g->out.off.p, g->out.tgt.p, n, r, d_comp);
+  k_cc_compress<<<grid, blk, 0, s>>>(d_comp, n);
+  g->timing.kernel_launches += 2 + sample_rounds;
+  // find_largest_component, wcc.rs:245-271 (which component is skipped never changes the result)
+  uint32_t skip = 0;
+  int use_skip = 0;
+  const uint32_t samples = (uint32_t)std::min<uint64_t>(cfg->sampling_size, 1u << 20);
+  if (samples > 0 && n > 0) {
+    DevBuf<uint32_t> d_samp;
+    GB_TRY(d_samp.alloc(samples));
+    k_cc_sample_labels<<<grid_for(samples, blk), blk, 0, s>>>(d_comp, n, samples, 0x5DEECE66Dull, d_samp.p);
+    std::vector<uint32_t> h(samples);
+    GB_CUDA(cudaMemcpyAsync(h.data(), d_samp.p, (size_t)samples * 4, cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    std::sort(h.begin(), h.end());
+    uint32_t best_cnt = 0, run = 0;
+    for (uint32_t i = 0; i < samples; ++i) {
+      run = (i > 0 && h[i] == h[i - 1]) ? run + 1 : 1;
+      if (run > best_cnt) {
+        best_cnt = run;
+        skip = h[i];
+      }
+    }
+    use_skip = 1;
+    g->timing.kernel_launches += 1;
+  }
+  // a sampled round count beyond 64 would leave out-edges [64, rounds) unprocessed in phase 1;
+  // link_remaining then starts from the rounds actually sampled so that every edge is seen
+  k_cc_link_remaining<<<grid_for((uint64_t)n, blk), blk, 0, s>>>(g->out.off.p, g->out.tgt.p, g->in.off.p,
+                                                               g->in.tgt.p, n, sample_rounds, skip, use_skip,
+                                                               d_comp);
+  k_cc_compress<<<grid, blk, 0, s>>>(d_comp, n);
+  g->timing.kernel_launches += 2;
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaEventRecord(g->ev_end, s));
+  if (h_comp) GB_CUDA(cudaMemcpyAsync(h_comp, d_comp, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+  float ms = 0.0f;
+  GB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
+  g->timing.total_ms = ms;
+  return GB_OK;
+}
+
+}  // namespace gb
+
+extern "C" {
+gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* components) {
+  GB_REQUIRE(components != nullptr, "components is NULL");
+  return gb::wcc_impl(graph, config, nullptr, components);
+}
+gb_status gb_wcc_device(const gb_graph* graph, const gb_wcc_config* config, uint32_t* d_components) {
+  GB_REQUIRE(d_components != nullptr, "d_components is NULL");
+  return gb::wcc_impl(graph, config, d_components, nullptr);
+}
+}

@@ -198,25 +198,37 @@ gb_status gb_sssp_device(const gb_graph* graph, const gb_sssp_config* config, fl
 gb_status gb_triangle_count(const gb_graph* graph, uint64_t* triangles);
 
 /* ---- multi-GPU PageRank shard (1-D edge-cut by destination range) ---------------------------
- * One process per GPU.  Rank p owns destination rows [row_begin,row_end) chosen by the
- * reference's in_degree_partition rule (graph_ops.rs:431-439, :479-509).  The caller (torch
- * distributed / NCCL) owns the exchange of the out_scores vector between steps. */
+ * One process per GPU (torch.distributed / NCCL own the plumbing).  The JACOBI path renumbers
+ * vertices internally (rows with in-edges first, then out-degree descending); shards are ranges of
+ * INTERNAL rows, identical on every rank because every rank derives them from the same graph.
+ * Rank p sweeps rows [ranges[p], ranges[p+1]) and owns that slice of the out_scores vector; the
+ * slices are exchanged once per sweep, either by the caller (NCCL allgather) or by the sweep
+ * kernel itself storing each finished value into the peers' next vectors (fused allgather). */
 typedef struct gb_pr_shard gb_pr_shard;
 
-/* ranges[0..parts] (parts+1 entries) for the graph's in-degree sequence */
+/* the reference's own partitioner on the ORIGINAL ids: in_degree_partition (graph_ops.rs:431-439,
+ * :479-509); ranges has parts+1 entries */
 gb_status gb_in_degree_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
-/* builds the shard state for rows [row_begin,row_end) of `graph`'s in-CSR */
+/* same greedy rule applied to the internal row order: ranges[0..parts] (parts+1 entries) */
+gb_status gb_pr_shard_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
 gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t row_begin, uint32_t row_end,
                              gb_pr_shard** shard);
-/* one Jacobi sweep over the shard's rows: reads the full d_x_cur[n], writes
- * d_x_next[row_begin..row_end) (pointer to the FULL next vector) and, when peers != NULL, also
- * stores the same slice into each d_peer_x_next[i] (peer-mapped full vectors: fused allgather).
- * d_scores_local: row_end-row_begin floats. d_error: one double, overwritten. */
-gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x_cur,
-                           float* d_scores_local);
-gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, const float* d_x_cur,
-                           float* d_x_next, float* const* d_peer_x_next, uint32_t peer_count,
-                           float* d_scores_local, double* d_error, void* cuda_stream);
+gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32_t* row_end,
+                           uint32_t* active_rows, uint64_t* edges);
+/* fills the full initial vectors (n floats each, internal order) on this rank: d_x0 = init/outdeg,
+ * the constant part of d_x1, d_scores = init */
+gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0, float* d_x1,
+                           float* d_scores, void* cuda_stream);
+/* one sweep (1-based sweep_no) over the shard's rows: reads the full d_x_cur[n], writes
+ * d_x_next[row_begin..row_end) and the same slice of every d_peer_x_next[i] (peer-mapped full
+ * vectors; peer_count may be 0), updates d_scores[row_begin..row_end) and stores this shard's share
+ * of the sweep error in *d_error.  All work is enqueued on cuda_stream (a cudaStream_t). */
+gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t sweep_no,
+                           const float* d_x_cur, float* d_x_next, float* const* d_peer_x_next,
+                           uint32_t peer_count, float* d_scores, double* d_error, void* cuda_stream);
+/* internal order -> original ids: d_scores_out[v] = d_scores_internal[new_id[v]] */
+gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_internal,
+                             float* d_scores_out, void* cuda_stream);
 gb_status gb_pr_shard_free(gb_pr_shard* shard);
 
 #ifdef __cplusplus

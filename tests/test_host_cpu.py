@@ -1,0 +1,108 @@
+"""CPU-side checks of the product package: the C-ABI library loads and exports every symbol the
+header declares, the host-side readers follow the reference formats, and — with no GPU in this
+container — every constructor fails loudly instead of falling back to a CPU path."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    text = (ROOT / "include" / "graph_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import graph_b200._capi as capi
+    names = header_functions()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(str(capi.LIB_PATH))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/graph_b200.h but not exported: {missing}"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(capi.SIGNATURES) == names
+    assert lib.gb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import graph_b200._capi as capi
+    assert ctypes.sizeof(capi.PageRankConfig) == 24
+    assert ctypes.sizeof(capi.WccConfig) == 24
+    assert ctypes.sizeof(capi.SsspConfig) == 16
+    assert ctypes.sizeof(capi.GraphInfo) == 40
+    assert ctypes.sizeof(capi.Timing) == 32
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    import graph_b200 as gb
+    assert gb.device_count() == 0
+    with pytest.raises(gb.GraphB200Error, match="no CUDA device"):
+        gb.DiGraph.from_numpy(np.array([[0, 1], [1, 2]], dtype=np.uint32))
+    with pytest.raises(gb.GraphB200Error, match="no CUDA device"):
+        gb.Graph.rmat(4)
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / "graph_b200").rglob("*.py"):
+        src = path.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, path
+
+
+def test_graph500_reader_matches_reference_format(golden_dir, goldens):
+    import graph_b200 as gb
+    import oracle
+    src, dst, n = gb._read_graph500(golden_dir / "scale_8.graph500")
+    osrc, odst, on = oracle.graph500_decode((golden_dir / "scale_8.graph500").read_bytes())
+    assert n == on == 256 and (src == osrc).all() and (dst == odst).all()
+    # ids above 32 bits are rejected like Idx::new (index.rs:51-54)
+    bad = np.array([1, 2, 0x00010000], dtype="<u4")
+    p = golden_dir.parent / "_tmp_bad.graph500"
+    bad.tofile(p)
+    try:
+        with pytest.raises(ValueError):
+            gb._read_graph500(p)
+    finally:
+        p.unlink()
+
+
+def test_edge_list_reader(golden_dir):
+    import graph_b200 as gb
+    import oracle
+    for name in ("test.el", "example.el", "windows.el"):
+        src, dst = gb._read_edge_list(golden_dir / name)
+        osrc, odst = oracle.edgelist_parse((golden_dir / name).read_bytes())
+        assert (src == osrc).all() and (dst == odst).all(), name
+    src, dst, w = gb._read_edge_list(golden_dir / "test.wel", with_values=True)
+    o = oracle.edgelist_parse((golden_dir / "test.wel").read_bytes(), with_values=True)
+    assert (src == o[0]).all() and (dst == o[1]).all() and (w == o[2]).all()
+
+
+def test_from_numpy_argument_checks():
+    import graph_b200 as gb
+    with pytest.raises(TypeError, match="2-dimensional array with at least 2 columns"):
+        gb._edges_from_numpy(np.array([1, 2, 3], dtype=np.uint32))
+    with pytest.raises(TypeError):
+        gb._edges_from_numpy(np.array([[1], [2]], dtype=np.uint32))
+    with pytest.raises(TypeError):
+        gb._edges_from_numpy(np.array([[0.5, 1.0]]))
+    s, d = gb._edges_from_numpy(np.array([[0, 1, 9], [2, 3, 9]], dtype=np.int64))
+    assert s.dtype == np.uint32 and s.tolist() == [0, 2] and d.tolist() == [1, 3]
+    assert gb._layout_value(None) == 0 and gb._layout_value(gb.Layout.Deduplicated) == 2
+    with pytest.raises(TypeError):
+        gb._layout_value("Sorted")
+
+
+def test_defaults_match_reference_configs():
+    import graph_b200 as gb
+    assert (gb.PageRankConfig().max_iterations, gb.PageRankConfig().tolerance,
+            gb.PageRankConfig().damping_factor) == (20, 1e-4, 0.85)  # page_rank.rs:46-48
+    w = gb.WccConfig()
+    assert (w.chunk_size, w.neighbor_rounds, w.sampling_size) == (16384, 2, 1024)  # wcc.rs:67-69
