@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py — PageRank GTEPS (edges/sec/iter) on synthetic RMAT, the headline metric of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scale S] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one graph: `page_rank` with 20 forced sweeps
+(tolerance 0, damping 0.85) on the RMAT scale-S graph (default 26 = the configuration the metric is
+quoted on; it fits one B200).  One JSON line is printed by rank 0.
+
+  value        m * sweeps * K / device time of K steps, graph resident in HBM, result left in HBM
+  e2e          same metric through the C ABI with HOST buffers: every step uploads the host CSR
+               (pinned), builds the device twin, runs page_rank and copies the ranks back
+  roofline     the dominant kernel (k_pr_pull) timed with CUDA events around every launch:
+               algorithmic bytes (4m + 24n + 4 per sweep) / mean launch time vs measured HBM peak
+  cpu_baseline the reference's multi-threaded in-place sweep (oracle.page_rank_mt, the C restatement
+               of crates/algos/src/page_rank.rs:113-168) on the same graph, bounded sample
+  --impl reference   times that CPU path alone, all host threads, same metric / config
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SWEEPS = 20
+DAMPING = 0.85
+SEED = 42
+EDGE_FACTOR = 16
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_empty(count: int, dtype):
+    """numpy view of pinned host memory (torch owns the allocation)."""
+    import torch
+    tdt = {np.uint32: torch.int32, np.float32: torch.float32}[dtype]
+    t = torch.empty(max(count, 1), dtype=tdt, pin_memory=torch.cuda.is_available())
+    return t, t.numpy().view(dtype)[:count]
+
+
+def algorithmic_bytes(n: int, m: int) -> int:
+    return 4 * m + 24 * n + 4  # BASELINE.md §3 / SURVEY.md §8(d)
+
+
+def cpu_leg(out_off, in_off, in_tgt, n, m, sweeps, threads=0):
+    """The reference's multi-threaded in-place sweep on the host cores (bounded sample)."""
+    import oracle
+    oracle.page_rank_mt(in_off, in_tgt, out_off, 1, 0.0, DAMPING, threads)  # warm-up sweep
+    t0 = time.perf_counter()
+    _, it, _ = oracle.page_rank_mt(in_off, in_tgt, out_off, sweeps, 0.0, DAMPING, threads)
+    dt = time.perf_counter() - t0
+    return m * it / dt / 1e9, dt, oracle.hardware_threads() if threads == 0 else threads
+
+
+def host_csr_from_device(g, pinned=True):
+    """(out_off, out_tgt, in_off, in_tgt) host copies of a DiGraph's CSR pair, pinned when possible."""
+    from graph_b200._capi import lib, check, CSR_OUT, CSR_IN
+    n, m = g.node_count(), g.edge_count()
+    keep, arrs = [], []
+    for which in (CSR_OUT, CSR_IN):
+        t_off, off = pinned_empty(n + 1, np.uint32)
+        t_tgt, tgt = pinned_empty(m, np.uint32)
+        check(lib.gb_graph_copy_csr(g._g, which, off.ctypes.data_as(C.c_void_p), tgt.ctypes.data_as(C.c_void_p), None))
+        keep += [t_off, t_tgt]
+        arrs += [off, tgt]
+    return arrs, keep
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Rust crate cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    scale, n = args.scale, 1 << args.scale
+    m = EDGE_FACTOR * n
+    # input preparation (untimed): the device generator/CSR builder when a GPU is present, else the
+    # oracle's own single-threaded builder
+    try:
+        import torch
+        import graph_b200 as gb
+        if not torch.cuda.is_available():
+            raise RuntimeError("no gpu")
+        g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
+        (out_off, _out_tgt, in_off, in_tgt), keep = host_csr_from_device(g, pinned=False)
+        del g
+        prep = "device generator + CSR build (untimed)"
+    except Exception:
+        src, dst = oracle.rmat_edges(scale, SEED)
+        out_off, _ = oracle.csr_build(src, dst, n, oracle.OUTGOING, oracle.SORTED)
+        in_off, in_tgt = oracle.csr_build(src, dst, n, oracle.INCOMING, oracle.SORTED)
+        prep = "oracle generator + CSR build (untimed)"
+    sample_sweeps = args.ref_sweeps
+    threads = oracle.hardware_threads()
+    for _ in range(args.warmup):
+        oracle.page_rank_mt(in_off, in_tgt, out_off, 1, 0.0, DAMPING, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.page_rank_mt(in_off, in_tgt, out_off, sample_sweeps, 0.0, DAMPING, 0)
+    dt = time.perf_counter() - t0
+    gteps = m * sample_sweeps * args.steps / dt / 1e9
+    sample = f"{sample_sweeps} of {SWEEPS} sweeps per step on the full RMAT scale-{scale} graph; input prep: {prep}"
+    line = {
+        "impl": "reference", "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(scale, 0),
+        "cpu_baseline": {"value": gteps, "unit": "GTEPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gteps, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(scale, n_gpus):
+    n = 1 << scale
+    return {"workload": f"page_rank f32, RMAT scale-{scale} (n={n}, m={EDGE_FACTOR * n}), {SWEEPS} sweeps forced "
+                        f"(tolerance 0), damping {DAMPING}, CsrLayout::Sorted, seed {SEED}",
+            "scale": scale, "sweeps": SWEEPS, "damping": DAMPING, "schedule": "jacobi",
+            "l2": "inputs larger than L2 (target stream >= 256 MiB per sweep), no explicit flush",
+            "parallelism": f"edge-cut x{n_gpus}" if n_gpus > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_single(args):
+    import torch
+    import graph_b200 as gb
+    from graph_b200 import _capi
+    from graph_b200._capi import lib, check
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(0)
+    gb.set_device(0)
+    scale, n = args.scale, 1 << args.scale
+    m = EDGE_FACTOR * n
+    g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
+    cfg = _capi.PageRankConfig(SWEEPS, 0.0, DAMPING, _capi.PR_JACOBI)
+    d_scores = torch.empty(n, dtype=torch.float32, device="cuda")
+    it, err = C.c_uint64(0), C.c_double(0.0)
+    stream = torch.cuda.ExternalStream(g.cuda_stream())
+
+    def step():
+        check(lib.gb_page_rank_device(g._g, C.byref(cfg), C.c_void_p(d_scores.data_ptr()), C.byref(it), C.byref(err)))
+        return g.last_timing()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            launches += step()["kernel_launches"]
+        ev1.record(stream)
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    assert it.value == SWEEPS
+    gteps = m * SWEEPS * args.steps / (ms * 1e-3) / 1e9
+
+    # dominant kernel, timed live with CUDA events around every launch (separate pass)
+    lib.gb_set_profiling(1)
+    hot_ms, hot_n = 0.0, 0
+    for _ in range(min(args.steps, 3)):
+        t = step()
+        hot_ms += t["hot_kernel_ms"]
+        hot_n += t["hot_kernel_launches"]
+    lib.gb_set_profiling(0)
+    peak, peak_src = peaks()
+    bytes_per_launch = algorithmic_bytes(n, m)
+    achieved = bytes_per_launch / (hot_ms / hot_n * 1e-3) / 1e9 if hot_n else 0.0
+    traffic = None
+    tp = ROOT / "profiles" / "pr_pull_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(f"scale{scale}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_pr_pull", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": hot_ms / max(hot_n, 1),
+                "kernel_share_of_step": (hot_ms / max(min(args.steps, 3), 1)) / (ms / args.steps)}
+
+    # e2e through the C ABI with host buffers (pinned): upload + device twin + page_rank + ranks back
+    (out_off, out_tgt, in_off, in_tgt), keep = host_csr_from_device(g)
+    del g
+    torch.cuda.empty_cache()
+    _, h_scores = pinned_empty(n, np.float32)
+    cfg_h = _capi.PageRankConfig(SWEEPS, 0.0, DAMPING, _capi.PR_JACOBI)
+
+    def e2e_step():
+        h = C.c_void_p()
+        check(lib.gb_digraph_from_csr_u32(0, n, out_off.ctypes.data_as(C.c_void_p), out_tgt.ctypes.data_as(C.c_void_p),
+                                          None, in_off.ctypes.data_as(C.c_void_p), in_tgt.ctypes.data_as(C.c_void_p),
+                                          C.byref(h)))
+        check(lib.gb_page_rank(h, C.byref(cfg_h), h_scores.ctypes.data_as(C.c_void_p), C.byref(it), C.byref(err)))
+        check(lib.gb_graph_free(h))
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e = {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS",
+           "h2d_bytes_per_step": int(8 * m + 8 * (n + 1)), "d2h_bytes_per_step": int(4 * n),
+           "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
+           "what": "gb_digraph_from_csr_u32(host CSR pair, pinned) + gb_page_rank(host scores) + gb_graph_free"}
+
+    # CPU baseline on the same graph, bounded sample
+    cpu = None
+    if not args.no_cpu:
+        v, dt, cores = cpu_leg(out_off, in_off, in_tgt, n, m, args.cpu_sweeps)
+        cpu = {"value": v, "unit": "GTEPS", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sweeps} in-place sweeps (after 1 warm-up sweep) of oracle.page_rank_mt on the "
+                         f"same RMAT scale-{scale} CSR, {dt:.2f} s"}
+
+    line = {
+        "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(scale, 1), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "hbm_roofline_gteps": peak * 1e9 / (bytes_per_launch / m) / 1e9,
+        "frac_of_hbm_roofline_whole_step": (bytes_per_launch * SWEEPS * args.steps / (ms * 1e-3) / 1e9) / peak,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_multi(args):
+    """N > 1: one process per GPU (torchrun), 1-D edge-cut, per-sweep exchange of the out_scores slices."""
+    import torch
+    import torch.distributed as dist
+    import graph_b200 as gb
+    from graph_b200.multigpu import ShardedPageRank
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    gb.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scale, n = args.scale, 1 << args.scale
+    m = EDGE_FACTOR * n
+    g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
+    spr = ShardedPageRank(g, exchange=args.exchange)
+    for _ in range(max(args.warmup, 3)):
+        spr.run(SWEEPS, DAMPING)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            spr.run(SWEEPS, DAMPING)
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    gteps = m * SWEEPS * args.steps / (ms * 1e-3) / 1e9
+    # e2e: ranks come back to the host every step
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        spr.run(SWEEPS, DAMPING)
+        host = spr.scores_host()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_dt = float(e2e_dt.item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {
+            "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {**workload_config(scale, world), "exchange": spr.exchange},
+            "clocks": clocks.summary(),
+            "e2e": {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 32,
+                    "d2h_bytes_per_step": int(4 * n), "steps": e2e_steps,
+                    "what": "sharded page_rank on resident shards + all ranks' scores copied to the host"},
+            "gpu_launches": int(spr.launches),
+            "roofline": {"bound": "hbm", "kernel": "k_pr_pull", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9 / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs, whole step incl. exchange"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--scale", type=int, default=26)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sweeps", type=int, default=3, help="sweeps of the CPU baseline sample")
+    ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_multi(args)
+    else:
+        run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -340,15 +340,27 @@ static gb_status upload_csr(cudaStream_t s, uint32_t n, const uint32_t* off, con
   return GB_OK;
 }
 
+// Host-side sanity of the offsets (O(n)); the O(m) target range check runs on the device after
+// the upload (k_check_ids) so that a billion-edge twin is not validated by one CPU thread.
 static gb_status validate_host_csr(uint32_t n, const uint32_t* off, const uint32_t* tgt, const char* what) {
   GB_REQUIRE(off != nullptr, "%s offsets is NULL", what);
   GB_REQUIRE(off[0] == 0, "%s offsets[0] must be 0", what);
   for (uint32_t v = 0; v < n; ++v)
     GB_REQUIRE(off[v] <= off[v + 1], "%s offsets not monotone at %u", what, v);
   GB_REQUIRE(off[n] == 0 || tgt != nullptr, "%s targets is NULL", what);
-  for (uint64_t i = 0; i < off[n]; ++i)
-    GB_REQUIRE(tgt[i] < n, "%s target %u at %llu out of range (n = %u)", what, tgt[i],
-               (unsigned long long)i, n);
+  return GB_OK;
+}
+
+static gb_status validate_device_targets(cudaStream_t s, uint32_t n, const DevCsr& c, const char* what) {
+  if (c.len == 0) return GB_OK;
+  DevBuf<unsigned int> bad;
+  GB_TRY(bad.alloc(1));
+  GB_CUDA(cudaMemsetAsync(bad.p, 0, 4, s));
+  k_check_ids<<<grid_for(c.len, 256), 256, 0, s>>>(c.tgt.p, c.len, n, bad.p);
+  unsigned int nbad = 0;
+  GB_CUDA(cudaMemcpyAsync(&nbad, bad.p, 4, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+  GB_REQUIRE(nbad == 0, "%s CSR holds %u targets >= node_count %u", what, nbad, n);
   return GB_OK;
 }
 
@@ -489,6 +501,8 @@ gb_status gb_digraph_from_csr_u32(int device, uint32_t n, const uint32_t* out_of
   GB_TRY(new_graph(device, GB_KIND_DIRECTED, n, &g));
   gb_status st = upload_csr(g->stream, n, out_off, out_tgt, out_w, &g->out);
   if (st == GB_OK) st = upload_csr(g->stream, n, in_off, in_tgt, nullptr, &g->in);
+  if (st == GB_OK) st = validate_device_targets(g->stream, n, g->out, "out");
+  if (st == GB_OK) st = validate_device_targets(g->stream, n, g->in, "in");
   if (st == GB_OK && cudaStreamSynchronize(g->stream) != cudaSuccess)
     st = fail(GB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (st != GB_OK) {
@@ -507,6 +521,7 @@ gb_status gb_graph_from_csr_u32(int device, uint32_t n, const uint32_t* off, con
   gb_graph* g = nullptr;
   GB_TRY(new_graph(device, GB_KIND_UNDIRECTED, n, &g));
   gb_status st = upload_csr(g->stream, n, off, tgt, nullptr, &g->out);
+  if (st == GB_OK) st = validate_device_targets(g->stream, n, g->out, "undirected");
   if (st == GB_OK && cudaStreamSynchronize(g->stream) != cudaSuccess)
     st = fail(GB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (st != GB_OK) {
