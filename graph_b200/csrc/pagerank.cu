@@ -28,10 +28,14 @@
 
 namespace gb {
 
-constexpr int PR_CHUNK = 256;   // merge-path items (edges + row ends) per warp task
-constexpr int PR_WARPS = 8;     // warps per CTA
+constexpr int PR_CHUNK = 252;      // merge-path items per warp task (edges + PR_ROW_COST per row end)
+constexpr int PR_ROW_COST = 8;     // items charged per row end: a chunk never ends more than 32 rows
+constexpr int PR_SLOTS = 256;      // register slots of a chunk: 8 consecutive edges per lane
+constexpr int PR_WARPS = 32;       // warps per CTA of the sweep kernel: one persistent CTA per SM
 constexpr int PR_THREADS = PR_WARPS * 32;
-constexpr int PR_LONG = 32;     // rows with >= PR_LONG staged values are reduced by the whole warp
+constexpr int PR_HOT = 52 * 1024;  // out_scores entries mirrored in shared memory (208 KB)
+constexpr int PR_WARP_SMEM = PR_SLOTS + 36 * 4;  // per warp: 256 head bytes + 36 row sums
+constexpr int PR_FIX_THREADS = 256;
 constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;
 
 // the merge-path chunking of a contiguous range of internal rows (the whole graph on one GPU, or
@@ -66,6 +70,8 @@ struct PrPlan {
   DevBuf<float> x[2];        // out_scores ping-pong [n]
   DevBuf<float> scores;      // ranks by internal id [n]
   PrRange all;               // chunking of every active row (single-GPU path)
+  uint32_t hot_count = 0;    // entries of out_scores mirrored in shared memory by the sweep kernel
+  size_t smem_bytes = 0;     // dynamic shared memory of the sweep kernel
   std::vector<cudaEvent_t> prof_events;
   uint64_t bytes() const {
     return new_id.bytes() + off.bytes() + tgt.bytes() + outdeg.bytes() + x[0].bytes() + x[1].bytes() +
@@ -86,6 +92,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint32_t* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -157,14 +168,23 @@ __global__ void k_merge_coords(const uint32_t* __restrict__ off, uint32_t row_be
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= num_chunks; k += gridDim.x * blockDim.x) {
     uint64_t diag = (uint64_t)k * PR_CHUNK;
     if (diag > items) diag = items;
-    diag += item_base;  // absolute position in the merged (row ends) x (edges) sequence
-    // r0 = first row whose end marker A[r] = off[r+1] + r is not before the diagonal
+    diag += item_base;  // absolute position in the merged sequence: row r's edges, then PR_ROW_COST slots
+    // r0 = first row whose end marker (first slot at off[r+1] + COST*r) is not before the diagonal
     uint32_t lo = row_begin, hi = row_end;
     while (lo < hi) {
       uint32_t mid = lo + (hi - lo) / 2;
-      if ((uint64_t)off[mid + 1] + mid < diag) lo = mid + 1; else hi = mid;
+      if ((uint64_t)off[mid + 1] + (uint64_t)PR_ROW_COST * mid < diag) lo = mid + 1; else hi = mid;
     }
-    coord[k] = make_uint2(lo, (uint32_t)(diag - lo));
+    // edges before the diagonal: all edges of rows < r0 plus the part of row r0 in front of it
+    uint32_t e;
+    if (lo >= row_end) {
+      e = off[row_end];
+    } else {
+      const int64_t want = (int64_t)diag - (int64_t)PR_ROW_COST * lo;
+      const int64_t b = off[lo], t = off[lo + 1];
+      e = (uint32_t)(want < b ? b : (want > t ? t : want));
+    }
+    coord[k] = make_uint2(lo, e);
   }
 }
 __global__ void k_fix_flags(const uint32_t* __restrict__ off, const uint2* __restrict__ coord,
@@ -186,6 +206,7 @@ struct PrArgs {
   float* x_next;
   float* peer_next[7];  // peer-mapped copies of x_next (fused allgather over NVLink); n_peers used
   uint32_t n_peers;
+  uint32_t hot_count;   // entries of x_cur mirrored in shared memory (multiple of 4)
   uint64_t item_base;
   float* scores;
   float* carry_tail;
@@ -215,96 +236,235 @@ __device__ __forceinline__ double pr_finalize(uint32_t r, float sum, const PrArg
   return fabs((double)__fsub_rn(nw, old));
 }
 
+// The sweep: one persistent CTA per SM.  The first PR_HOT entries of out_scores — the most gathered
+// sources, contiguous thanks to the out-degree ordering — are mirrored in shared memory once per
+// sweep; gathers of those ids are shared-memory loads (bank-limited, ~10 per clock per SM) instead
+// of divergent global loads (L1TEX accepts ~0.57 sectors per clock per SM: the measured ceiling of
+// the first version of this kernel).  Targets are read with lane-consecutive 32-bit loads so that
+// one gather instruction covers 32 consecutive entries of a sorted row and coalesces wherever a
+// row's sources are dense.
+struct RowMeta {
+  uint32_t os, oe, deg;
+  float old;
+};
+// offsets / out-degree / old score of the rows ending in a chunk (one row per lane, at most 32)
+__device__ __forceinline__ RowMeta pr_load_meta(const PrArgs& a, uint32_t r0, uint32_t r1, uint32_t lane) {
+  RowMeta m{0u, 0u, 1u, 0.0f};
+  const uint32_t r = r0 + lane;
+  if (r < r1) {
+    m.os = a.off[r];
+    m.oe = a.off[r + 1];
+    m.deg = a.outdeg[r];
+    m.old = a.scores[r];
+  }
+  return m;
+}
+// 8 consecutive targets per lane (two aligned 128-bit loads); slots outside [e0, e1) become ~0
+__device__ __forceinline__ void pr_load_targets(const uint32_t* __restrict__ tgt, uint32_t e0, uint32_t e1,
+                                                uint32_t lane, uint32_t (&t)[8]) {
+  const uint32_t i0 = (e0 & ~3u) + 8 * lane;
+  uint4 ta = make_uint4(~0u, ~0u, ~0u, ~0u), tb = ta;
+  if (i0 < e1) ta = ld_stream_u4(tgt + i0);
+  if (i0 + 4 < e1) tb = ld_stream_u4(tgt + i0 + 4);
+  t[0] = ta.x; t[1] = ta.y; t[2] = ta.z; t[3] = ta.w;
+  t[4] = tb.x; t[5] = tb.y; t[6] = tb.z; t[7] = tb.w;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (i0 + j < e0 || i0 + j >= e1) t[j] = ~0u;
+}
+__device__ __forceinline__ void pr_gather(const float* __restrict__ x, const float* hot, uint32_t hot_n,
+                                          const uint32_t (&t)[8], float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t tj = t[j];
+    float val = 0.0f;
+    if (tj < hot_n) val = hot[tj];
+    else if (tj != ~0u) val = __ldg(x + tj);
+    v[j] = val;
+  }
+}
+
 template <bool PEERS>
-__global__ void __launch_bounds__(PR_THREADS) k_pr_pull(const PrArgs a) {
-  __shared__ __align__(16) float stage[PR_WARPS][PR_CHUNK + 8];
+__device__ __forceinline__ double pr_update(uint32_t r, float sum, float old, uint32_t deg, const PrArgs& a) {
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damping, sum));
+  a.scores[r] = nw;
+  const float xo = __fdiv_rn(nw, (float)deg);
+  a.x_next[r] = xo;
+  if (PEERS)
+    for (uint32_t p = 0; p < a.n_peers; ++p) a.peer_next[p][r] = xo;
+  return fabs((double)__fsub_rn(nw, old));
+}
+
+// The sweep: one persistent CTA per SM.
+//  * The first PR_HOT entries of out_scores — the most gathered sources, contiguous thanks to the
+//    out-degree ordering — are mirrored in shared memory once per sweep; gathers of those ids are
+//    shared-memory loads instead of divergent global loads (L1TEX accepts only ~0.57 divergent
+//    sectors per clock per SM: the measured ceiling of the first version of this kernel).
+//  * A chunk is <= 252 consecutive edges and <= 32 row ends.  Each lane owns 8 consecutive edges
+//    (two 128-bit loads of the target stream), gathers them into registers, sums its own run
+//    between row boundaries and one warp-level segmented scan joins the runs across lanes; the row
+//    totals meet their rows (one lane per row, metadata prefetched) through 33 floats of smem.
+//  * Two-deep software pipeline: while chunk k is reduced, the gathers of chunk k+1, the targets of
+//    chunk k+2 and the coordinates of chunk k+3 are already in flight.
+template <bool PEERS>
+__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_pull(const PrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* hot = smem;  // [hot_count]
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(smem + a.hot_count);
   __shared__ double warp_err[PR_WARPS];
   if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s = stage[warp];
+  unsigned char* heads = warp_base + warp * PR_WARP_SMEM;            // [256] row id + 1 at the slot a row starts
+  float* rs = reinterpret_cast<float*>(heads + PR_SLOTS);            // [36] row totals of this chunk
   const float* __restrict__ x = a.x_cur;
+  const uint32_t hot_n = a.hot_count;
+  for (uint32_t i = threadIdx.x * 4; i < hot_n; i += PR_THREADS * 4)
+    *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
+  __syncthreads();
   double err = 0.0;
 
-  for (uint32_t k = blockIdx.x * PR_WARPS + warp; k < a.num_chunks; k += gridDim.x * PR_WARPS) {
-    const uint2 c0 = a.coord[k], c1 = a.coord[k + 1];
+  const uint32_t stride = gridDim.x * PR_WARPS;
+  const uint32_t K = a.num_chunks;
+  uint32_t k = blockIdx.x * PR_WARPS + warp;
+  uint2 c0 = make_uint2(0, 0), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
+  uint32_t t[8];
+  float v[8];
+  RowMeta cur{0u, 0u, 1u, 0.0f}, nxt = cur;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    t[j] = ~0u;
+    v[j] = 0.0f;
+  }
+  if (k < K) {
+    c0 = a.coord[k];
+    c1 = a.coord[k + 1];
+    if (k + stride < K) {
+      n0 = a.coord[k + stride];
+      n1 = a.coord[k + stride + 1];
+    }
+    if (k + 2 * stride < K) {
+      m0 = a.coord[k + 2 * stride];
+      m1 = a.coord[k + 2 * stride + 1];
+    }
+    pr_load_targets(a.tgt, c0.y, c1.y, lane, t);
+    cur = pr_load_meta(a, c0.x, c1.x, lane);
+    pr_gather(x, hot, hot_n, t, v);
+    if (k + stride < K) pr_load_targets(a.tgt, n0.y, n1.y, lane, t);
+  }
+  while (k < K) {
     const uint32_t r0 = c0.x, e0 = c0.y, r1 = c1.x, e1 = c1.y;
     const uint32_t a0 = e0 & ~3u;
+    const uint32_t nr = r1 - r0;  // rows ending in this chunk (<= 32)
+    const uint32_t kn = k + stride, knn = kn + stride;
 
-    if (r0 == r1) {
-      // the whole chunk lies inside one (long) row: pure streaming reduction, no staging
-      float acc = 0.0f;
-      for (uint32_t idx = a0 + 4 * lane; idx < e1; idx += 128) {
-        uint4 t = ld_stream_u4(a.tgt + idx);
-        float v0 = __ldg(x + t.x), v1 = __ldg(x + t.y), v2 = __ldg(x + t.z), v3 = __ldg(x + t.w);
-        v0 = (idx + 0 >= e0 && idx + 0 < e1) ? v0 : 0.0f;
-        v1 = (idx + 1 >= e0 && idx + 1 < e1) ? v1 : 0.0f;
-        v2 = (idx + 2 >= e0 && idx + 2 < e1) ? v2 : 0.0f;
-        v3 = (idx + 3 >= e0 && idx + 3 < e1) ? v3 : 0.0f;
-        acc += (v0 + v1) + (v2 + v3);
+    // ---- heads: where does each row of this chunk start among the 256 slots? -----------------
+    uint32_t seg_s = 0, seg_e = 0;
+    bool tail_exists = false;
+    if (nr) {
+      *reinterpret_cast<uint2*>(heads + 8 * lane) = make_uint2(0u, 0u);
+      __syncwarp();
+      if (lane < nr) {
+        seg_s = cur.os > e0 ? cur.os : e0;
+        seg_e = cur.oe;
+        if (seg_e > seg_s) heads[seg_s - a0] = (unsigned char)(lane + 1);
       }
-      acc = warp_sum(acc);
+      // the row that continues into the next chunk starts where the last ending row stops
+      const uint32_t last_oe = __shfl_sync(0xFFFFFFFFu, cur.oe, nr - 1);
+      tail_exists = last_oe < e1;
+      if (lane == 0 && tail_exists) heads[last_oe - a0] = (unsigned char)(nr + 1);
+      __syncwarp();
+    }
+
+    // ---- lane-local runs between row starts -----------------------------------------------------
+    float run = 0.0f, head_sum = 0.0f;
+    uint32_t first_f = 0, prev_f = 0;
+    if (nr) {
+      const uint2 hb = *reinterpret_cast<const uint2*>(heads + 8 * lane);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t f = ((j < 4 ? hb.x : hb.y) >> (8 * (j & 3))) & 0xFFu;
+        if (f) {
+          if (prev_f == 0) {
+            head_sum = run;  // belongs to the run entering this lane
+            first_f = f;
+          } else {
+            rs[prev_f - 1] = run;  // a row that starts and ends inside this lane
+          }
+          prev_f = f;
+          run = 0.0f;
+        }
+        run += v[j];
+      }
+    } else {
+      run = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+
+    // ---- v is consumed: issue the next chunk's gathers and the loads behind them ---------------
+    uint2 q0 = make_uint2(0, 0), q1 = q0;
+    if (kn < K) {
+      pr_gather(x, hot, hot_n, t, v);
+      nxt = pr_load_meta(a, n0.x, n1.x, lane);
+      if (knn < K) {
+        pr_load_targets(a.tgt, m0.y, m1.y, lane, t);
+        if (knn + stride < K) {
+          q0 = a.coord[knn + stride];
+          q1 = a.coord[knn + stride + 1];
+        }
+      }
+    }
+
+    if (nr == 0) {
+      // the whole chunk lies inside one (long) row
+      const float acc = warp_sum(run);
       if (lane == 0) a.carry_tail[k] = acc;
-      continue;
+    } else {
+      // ---- segmented inclusive scan of the lane runs (a lane with a row start blocks the carry) --
+      const unsigned flagged = __ballot_sync(0xFFFFFFFFu, prev_f != 0);
+      float val = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float up = __shfl_up_sync(0xFFFFFFFFu, val, d);
+        // lanes (lane-d, lane] must hold no row start for the carry to pass
+        const unsigned window = (lane >= (uint32_t)d) ? ((flagged >> (lane - d + 1)) & ((1u << d) - 1u)) : 1u;
+        if (window == 0) val += up;
+      }
+      float carry_in = __shfl_up_sync(0xFFFFFFFFu, val, 1);
+      if (lane == 0) carry_in = 0.0f;
+      // the run that entered this lane ends at its first row start: it is row first_f - 2
+      if (first_f >= 2) rs[first_f - 2] = carry_in + head_sum;
+      // the last run of the chunk: total sits in lane 31, its row id in the last flagged lane
+      const int last_lane = 31 - __clz(flagged);  // flagged != 0: row 0 or row 1 starts in this chunk
+      const uint32_t last_f = __shfl_sync(0xFFFFFFFFu, prev_f, last_lane);
+      if (lane == 31 && last_f) rs[last_f - 1] = val;
+      __syncwarp();
+      // ---- one lane per row: finish it ----------------------------------------------------------
+      if (lane < nr) {
+        const float sum = (seg_e > seg_s) ? rs[lane] : 0.0f;
+        if (cur.os < e0) a.head_part[k] = sum;  // row began in an earlier chunk: fix-up kernel finishes it
+        else err += pr_update<PEERS>(r0 + lane, sum, cur.old, cur.deg, a);
+      }
+      if (lane == 0) a.carry_tail[k] = tail_exists ? rs[nr] : 0.0f;
+      __syncwarp();
     }
 
-    // phase 1: stream targets, gather, stage (entries outside [e0,e1) are staged but never read;
-    // the target array carries 8 zeroed slack entries so every gather index is a valid vertex)
-    for (uint32_t idx = a0 + 4 * lane; idx < e1; idx += 128) {
-      uint4 t = ld_stream_u4(a.tgt + idx);
-      float4 v;
-      v.x = __ldg(x + t.x);
-      v.y = __ldg(x + t.y);
-      v.z = __ldg(x + t.z);
-      v.w = __ldg(x + t.w);
-      *reinterpret_cast<float4*>(s + (idx - a0)) = v;
-    }
-    __syncwarp();
-
-    // phase 2: reduce the rows that end in this chunk, plus the tail of the row that continues
-    for (uint32_t rb = r0; rb <= r1; rb += 32) {
-      const uint32_t r = rb + lane;
-      const bool is_row = r < r1;
-      const bool is_tail = (r == r1);
-      uint32_t os = e1, seg_s = 0, seg_e = 0;
-      if (is_row || (is_tail && r < a.row_end)) {
-        os = a.off[r];
-        seg_s = os > e0 ? os : e0;
-        seg_e = is_tail ? e1 : a.off[r + 1];
-      }
-      const uint32_t len = seg_e - seg_s;
-      float sum = 0.0f;
-      if (len < PR_LONG) {
-        for (uint32_t j = seg_s; j < seg_e; ++j) sum += s[j - a0];
-      }
-      unsigned long_mask = __ballot_sync(0xFFFFFFFFu, len >= PR_LONG);
-      while (long_mask) {
-        const int owner = __ffs(long_mask) - 1;
-        long_mask &= long_mask - 1;
-        const uint32_t ss = __shfl_sync(0xFFFFFFFFu, seg_s, owner);
-        const uint32_t se = __shfl_sync(0xFFFFFFFFu, seg_e, owner);
-        float p = 0.0f;
-        for (uint32_t j = ss + lane; j < se; j += 32) p += s[j - a0];
-        p = warp_sum(p);
-        if ((int)lane == owner) sum = p;
-      }
-      if (is_row) {
-        if (os < e0) a.head_part[k] = sum;  // row began in an earlier chunk: fix-up kernel finishes it
-        else err += pr_finalize<PEERS>(r, sum, a);
-      } else if (is_tail) {
-        a.carry_tail[k] = sum;
-      }
-    }
-    __syncwarp();
+    k = kn;
+    c0 = n0;
+    c1 = n1;
+    n0 = m0;
+    n1 = m1;
+    m0 = q0;
+    m1 = q1;
+    cur = nxt;
   }
 
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0;
+    double tt = 0.0;
 #pragma unroll
-    for (int w = 0; w < PR_WARPS; ++w) t += warp_err[w];
-    a.block_err[blockIdx.x] = t;
+    for (int w = 0; w < PR_WARPS; ++w) tt += warp_err[w];
+    a.block_err[blockIdx.x] = tt;
   }
 }
 
@@ -312,23 +472,41 @@ __global__ void __launch_bounds__(PR_THREADS) k_pr_pull(const PrArgs a) {
 // CTA to finish, reduces the error of the sweep in a fixed order and evaluates the stop rule of
 // page_rank.rs:107.
 template <bool PEERS>
-__global__ void __launch_bounds__(PR_THREADS) k_pr_fix(const PrArgs a) {
-  __shared__ double warp_err[PR_WARPS];
+__global__ void __launch_bounds__(PR_FIX_THREADS) k_pr_fix(const PrArgs a) {
+  constexpr int FIX_WARPS = PR_FIX_THREADS / 32;
+  __shared__ double warp_err[FIX_WARPS];
   __shared__ bool is_last;
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double err = 0.0;
-  for (uint32_t i = blockIdx.x * PR_WARPS + warp; i < a.num_fix; i += gridDim.x * PR_WARPS) {
-    const uint32_t k = a.fix[i];
-    const uint32_t r0 = a.coord[k].x;
-    const uint32_t j0 = (uint32_t)(((uint64_t)a.off[r0] + r0 - a.item_base) / PR_CHUNK);  // chunk holding the row's first edge
-    float p = 0.0f;
-    for (uint32_t j = j0 + lane; j < k; j += 32) p += a.carry_tail[j];
-    p = warp_sum(p);
-    if (lane == 0) {
-      float sum = p + a.head_part[k];
-      err += pr_finalize<PEERS>(r0, sum, a);
+  const uint32_t nthreads = gridDim.x * PR_FIX_THREADS;
+  // one lane per straddling row; rows spanning many chunks (hubs) are summed by the whole warp
+  for (uint32_t ib = blockIdx.x * PR_FIX_THREADS + warp * 32; ib < a.num_fix; ib += nthreads) {
+    const uint32_t i = ib + lane;
+    const bool live = i < a.num_fix;
+    uint32_t k = 0, r0 = 0, j0 = 0;
+    if (live) {
+      k = a.fix[i];
+      r0 = a.coord[k].x;
+      j0 = (uint32_t)(((uint64_t)a.off[r0] + (uint64_t)PR_ROW_COST * r0 - a.item_base) / PR_CHUNK);  // chunk holding the row's first edge
     }
+    const uint32_t span = k - j0;
+    const bool is_long = live && span > 8;
+    float p = 0.0f;
+    if (live && !is_long)
+      for (uint32_t j = j0; j < k; ++j) p += a.carry_tail[j];
+    unsigned long_mask = __ballot_sync(0xFFFFFFFFu, is_long);
+    while (long_mask) {
+      const int owner = __ffs(long_mask) - 1;
+      long_mask &= long_mask - 1;
+      const uint32_t oj = __shfl_sync(0xFFFFFFFFu, j0, owner);
+      const uint32_t ok = __shfl_sync(0xFFFFFFFFu, k, owner);
+      float q = 0.0f;
+      for (uint32_t j = oj + lane; j < ok; j += 32) q += a.carry_tail[j];
+      q = warp_sum(q);
+      if ((int)lane == owner) p = q;
+    }
+    if (live) err += pr_finalize<PEERS>(r0, p + a.head_part[k], a);
   }
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
@@ -336,7 +514,7 @@ __global__ void __launch_bounds__(PR_THREADS) k_pr_fix(const PrArgs a) {
   if (threadIdx.x == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < PR_WARPS; ++w) t += warp_err[w];
+    for (int w = 0; w < FIX_WARPS; ++w) t += warp_err[w];
     a.block_err[a.grid_pull + blockIdx.x] = t;
     __threadfence();
     unsigned ticket = atomicAdd(&a.ctrl[1], 1u);
@@ -348,14 +526,14 @@ __global__ void __launch_bounds__(PR_THREADS) k_pr_fix(const PrArgs a) {
   // fixed-order reduction of all CTA partials (deterministic error)
   const uint32_t total = a.grid_pull + gridDim.x;
   double t = 0.0;
-  for (uint32_t i = threadIdx.x; i < total; i += PR_THREADS) t += ((volatile double*)a.block_err)[i];
+  for (uint32_t i = threadIdx.x; i < total; i += PR_FIX_THREADS) t += ((volatile double*)a.block_err)[i];
   t = warp_sum(t);
   if (lane == 0) warp_err[warp] = t;
   __syncthreads();
   if (threadIdx.x == 0) {
     double e = a.extra_err;
 #pragma unroll
-    for (int w = 0; w < PR_WARPS; ++w) e += warp_err[w];
+    for (int w = 0; w < FIX_WARPS; ++w) e += warp_err[w];
     a.err_hist[a.sweep] = e;
     a.ctrl[1] = 0;
     if (e < a.tolerance) a.ctrl[0] = a.sweep_no;
@@ -450,8 +628,8 @@ static gb_status build_range(const gb_graph* g, const PrPlan* p, uint32_t row_be
   GB_CUDA(cudaMemcpyAsync(&h_off[0], p->off.p + row_begin, 4, cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(&h_off[1], p->off.p + row_end, 4, cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaStreamSynchronize(s));
-  r->item_base = (uint64_t)h_off[0] + row_begin;
-  const uint64_t items = (uint64_t)(h_off[1] - h_off[0]) + (row_end - row_begin);
+  r->item_base = (uint64_t)h_off[0] + (uint64_t)PR_ROW_COST * row_begin;
+  const uint64_t items = (uint64_t)(h_off[1] - h_off[0]) + (uint64_t)PR_ROW_COST * (row_end - row_begin);
   const uint64_t nchunks = (items + PR_CHUNK - 1) / PR_CHUNK;
   GB_REQUIRE(nchunks < 0xFFFFFFF0ull, "too many chunks");
   r->num_chunks = (uint32_t)nchunks;
@@ -477,14 +655,12 @@ static gb_status build_range(const gb_graph* g, const PrPlan* p, uint32_t row_be
     GB_CUDA(cudaMemcpyAsync(&r->num_fix, d_num.p, 4, cudaMemcpyDeviceToHost, s));
     GB_CUDA(cudaStreamSynchronize(s));
   }
-  int dev_sms = 148, per_sm = 1;
+  int dev_sms = 148;
   GB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
-  GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pr_pull<false>, PR_THREADS, 0));
-  if (per_sm < 1) per_sm = 1;
   const uint64_t want = ((uint64_t)r->num_chunks + PR_WARPS - 1) / PR_WARPS;
-  r->grid_pull = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)dev_sms * per_sm));
-  const uint64_t want_fix = ((uint64_t)r->num_fix + PR_WARPS - 1) / PR_WARPS;
-  r->grid_fix = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fix, (uint64_t)dev_sms * 2));
+  r->grid_pull = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)dev_sms));  // 1 CTA / SM
+  const uint64_t want_fix = ((uint64_t)r->num_fix + PR_FIX_THREADS - 1) / PR_FIX_THREADS;
+  r->grid_fix = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fix, (uint64_t)dev_sms * 8));
   GB_TRY(r->block_err.alloc((size_t)r->grid_pull + r->grid_fix));
   GB_TRY(r->err_hist.alloc(64));
   GB_TRY(r->ctrl.alloc(2));
@@ -573,6 +749,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       // empty only if m == 0
       p->n_active = (m == 0) ? 0 : lo;
     }
+    p->hot_count = std::min<uint32_t>((uint32_t)PR_HOT, n & ~3u);
+    p->smem_bytes = (size_t)p->hot_count * sizeof(float) + (size_t)PR_WARPS * PR_WARP_SMEM;
+    GB_CUDA(cudaFuncSetAttribute(k_pr_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     // 4. chunking of the whole active range + state vectors
     GB_TRY(build_range(g, p, 0, p->n_active, &p->all));
     GB_TRY(p->x[0].alloc(n));
@@ -610,6 +790,7 @@ static PrArgs make_args(const PrPlan* p, const PrRange* rg, float base, float da
   a.damping = damping;
   a.tolerance = tolerance;
   a.n_peers = 0;
+  a.hot_count = p->hot_count;
   return a;
 }
 
@@ -685,9 +866,9 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
         ev_used += 2;
         GB_CUDA(cudaEventRecord(e0, s));
       }
-      if (rg->num_chunks) k_pr_pull<false><<<rg->grid_pull, PR_THREADS, 0, s>>>(a);
+      if (rg->num_chunks) k_pr_pull<false><<<rg->grid_pull, PR_THREADS, p->smem_bytes, s>>>(a);
       if (e1) GB_CUDA(cudaEventRecord(e1, s));
-      k_pr_fix<false><<<rg->grid_fix, PR_THREADS, 0, s>>>(a);
+      k_pr_fix<false><<<rg->grid_fix, PR_FIX_THREADS, 0, s>>>(a);
       g->timing.kernel_launches += rg->num_chunks ? 2 : 1;
       if (sweep_no == 1 && p->n_active < n) {
         // sources without in-edges change exactly once (init/deg -> base/deg): patch the buffer
@@ -881,11 +1062,11 @@ gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t swe
                     ? (double)(p->n - p->n_active) * fabs((double)(base - init))
                     : 0.0;
   if (peer_count) {
-    if (rg->num_chunks) gb::k_pr_pull<true><<<rg->grid_pull, gb::PR_THREADS, 0, s>>>(a);
-    gb::k_pr_fix<true><<<rg->grid_fix, gb::PR_THREADS, 0, s>>>(a);
+    if (rg->num_chunks) gb::k_pr_pull<true><<<rg->grid_pull, gb::PR_THREADS, p->smem_bytes, s>>>(a);
+    gb::k_pr_fix<true><<<rg->grid_fix, gb::PR_FIX_THREADS, 0, s>>>(a);
   } else {
-    if (rg->num_chunks) gb::k_pr_pull<false><<<rg->grid_pull, gb::PR_THREADS, 0, s>>>(a);
-    gb::k_pr_fix<false><<<rg->grid_fix, gb::PR_THREADS, 0, s>>>(a);
+    if (rg->num_chunks) gb::k_pr_pull<false><<<rg->grid_pull, gb::PR_THREADS, p->smem_bytes, s>>>(a);
+    gb::k_pr_fix<false><<<rg->grid_fix, gb::PR_FIX_THREADS, 0, s>>>(a);
   }
   if (sweep_no == 1 && p->n_active < p->n)
     gb::k_pr_fill_inactive<<<gb::grid_for(p->n - p->n_active, 256), 256, 0, s>>>(
