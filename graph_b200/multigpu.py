@@ -1,0 +1,177 @@
+"""Multi-GPU PageRank: 1-D edge-cut across the GPUs of one box, one process per GPU.
+
+The reference has no distributed code at all; this is the one exchange step
+BASELINE.json's north_star adds: every rank sweeps the destination rows of its shard
+(`gb_pr_shard_step`) and the per-sweep out_scores slices are exchanged either
+
+  * "peer"  — fused: the sweep kernel stores each finished out_score straight into every peer's
+              next vector through NVLink peer mappings (torch symmetric memory supplies the
+              pointers); the 8-byte all-reduce of the sweep error is the only collective and doubles
+              as the inter-sweep barrier, or
+  * "nccl"  — baseline: one NCCL broadcast per shard slice after the kernel.
+
+Shards are ranges of INTERNAL rows (the JACOBI path's renumbering), chosen by the reference's own
+greedy in-degree rule (crates/builder/src/graph_ops.rs:431-439, :479-509) so every rank derives the
+same ranges without talking to anyone.  `torch.distributed` is plumbing only; the compute is the
+same CUDA kernel as on one GPU.  The compute backend is injectable so that the orchestration
+(partition, exchange, stop rule, assembly) is testable with gloo on CPUs (tests/test_multigpu_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import check, lib
+
+
+class CudaShardBackend:
+    """The product backend: gb_pr_shard_* of libgraph_b200.so on this rank's GPU."""
+
+    def __init__(self, graph, rank: int, world: int):
+        self.graph = graph
+        self.n = graph.node_count()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        ranges = np.zeros(world + 1, np.uint32)
+        check(lib.gb_pr_shard_partition(graph._g, world, ranges.ctypes.data_as(C.c_void_p)))
+        self.ranges = [int(v) for v in ranges]
+        self._shard = C.c_void_p()
+        check(lib.gb_pr_shard_create(graph._g, self.ranges[rank], self.ranges[rank + 1], C.byref(self._shard)))
+        rb, re, act = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        check(lib.gb_pr_shard_info(self._shard, C.byref(rb), C.byref(re), C.byref(act), None))
+        self.n_active = int(act.value)
+        self.launches = 0
+
+    def __del__(self):
+        sh, self._shard = getattr(self, "_shard", None), None
+        if sh:
+            try:
+                lib.gb_pr_shard_free(sh)
+            except Exception:
+                pass
+
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def init(self, damping, x0, x1, scores):
+        check(lib.gb_pr_shard_init(self._shard, damping, C.c_void_p(x0.data_ptr()), C.c_void_p(x1.data_ptr()),
+                                   C.c_void_p(scores.data_ptr()), self._stream()))
+        self.launches += 1
+
+    def step(self, damping, sweep_no, x_cur, x_next, peer_ptrs, scores, err):
+        arr = None
+        if peer_ptrs:
+            arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        check(lib.gb_pr_shard_step(self._shard, damping, sweep_no, C.c_void_p(x_cur.data_ptr()),
+                                   C.c_void_p(x_next.data_ptr()), arr, len(peer_ptrs or ()),
+                                   C.c_void_p(scores.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()))
+        self.launches += 3 if sweep_no == 1 else 2
+
+    def finish(self, scores_internal):
+        out = torch.empty_like(scores_internal)
+        check(lib.gb_pr_shard_finish(self._shard, C.c_void_p(scores_internal.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     self._stream()))
+        self.launches += 1
+        return out
+
+
+class ShardedPageRank:
+    """page_rank over `world` shards; every rank ends up with the full score vector.
+
+    run(max_iterations, damping, tolerance) follows page_rank.rs:88-110: sweep, error = sum over all
+    ranks, stop when error < tolerance or the sweep count reaches max_iterations.
+    """
+
+    def __init__(self, graph=None, exchange: str = "auto", backend=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.backend = backend if backend is not None else CudaShardBackend(graph, self.rank, self.world)
+        b = self.backend
+        self.n, self.n_active, self.ranges = b.n, b.n_active, b.ranges
+        dev = b.device
+        self.exchange = "nccl"
+        self._peer_next = [None, None]
+        self.x = None
+        if exchange in ("auto", "peer") and dev.type == "cuda" and self.world > 1:
+            try:
+                self._setup_symmetric(dev)
+                self.exchange = "peer"
+            except Exception as exc:  # symmetric memory unavailable: fall back to the NCCL exchange
+                if exchange == "peer":
+                    raise
+                self._symm_error = repr(exc)
+        if self.x is None:
+            self.x = [torch.empty(self.n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.scores = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.ran_iterations = 0
+        self.error = 0.0
+
+    # -- symmetric memory (NVLink peer mappings) --
+    def _setup_symmetric(self, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        group_name = (self.group or dist.group.WORLD).group_name
+        buf = symm_mem.empty(2 * self.n, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, group_name)
+        self._symm = (buf, hdl)
+        self.x = [buf[: self.n], buf[self.n:]]
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        for which in (0, 1):
+            self._peer_next[which] = [ptrs[p] + which * self.n * 4 for p in range(self.world) if p != self.rank]
+
+    @property
+    def launches(self) -> int:
+        return getattr(self.backend, "launches", 0)
+
+    def _exchange(self, x_next):
+        if self.exchange == "peer":
+            return  # the kernel already stored the slice into every peer
+        for p in range(self.world):
+            lo, hi = min(self.ranges[p], self.n_active), min(self.ranges[p + 1], self.n_active)
+            if hi > lo:
+                dist.broadcast(x_next[lo:hi], src=dist.get_global_rank(self.group, p) if self.group else p,
+                               group=self.group)
+
+    def run(self, max_iterations: int = 20, damping: float = 0.85, tolerance: float = 0.0):
+        b = self.backend
+        b.init(damping, self.x[0], self.x[1], self.scores)
+        if self.exchange == "peer":
+            dist.barrier(group=self.group)  # nobody may store into a peer that is still initialising
+        sweep = 0
+        limit = max_iterations if max_iterations else 100000
+        while True:
+            sweep += 1
+            cur, nxt = self.x[(sweep - 1) & 1], self.x[sweep & 1]
+            peers = self._peer_next[sweep & 1] if self.exchange == "peer" else None
+            b.step(damping, sweep, cur, nxt, peers, self.scores, self.err)
+            self._exchange(nxt)
+            # total error of the sweep; also the barrier that orders the peer stores of sweep k before
+            # any rank's reads in sweep k+1
+            dist.all_reduce(self.err, op=dist.ReduceOp.SUM, group=self.group)
+            if tolerance > 0.0:
+                self.error = float(self.err.item())
+                if self.error < tolerance:
+                    break
+            if sweep == limit:
+                break
+        self.ran_iterations = sweep
+        if not tolerance > 0.0:
+            self.error = float(self.err.item())
+        return self
+
+    def scores_device(self):
+        """Full score vector in original ids on this rank's device (exchanges the score slices)."""
+        for p in range(self.world):
+            lo, hi = min(self.ranges[p], self.n_active), min(self.ranges[p + 1], self.n_active)
+            if hi > lo:
+                dist.broadcast(self.scores[lo:hi], src=dist.get_global_rank(self.group, p) if self.group else p,
+                               group=self.group)
+        return self.backend.finish(self.scores)
+
+    def scores_host(self) -> np.ndarray:
+        return self.scores_device().cpu().numpy()

@@ -1,0 +1,65 @@
+"""Multi-GPU PageRank (1-D edge-cut, one process per GPU, NCCL) against the oracle.  Needs >= 2 GPUs;
+run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, scale, exchange, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import graph_b200 as gb
+        from graph_b200.multigpu import ShardedPageRank
+        gb.set_device(rank)
+        g = gb.DiGraph.rmat(scale, seed=42, layout=gb.Layout.Sorted)
+        spr = ShardedPageRank(g, exchange=exchange)
+        out = []
+        for maxit, tol in ((20, 0.0), (60, 1e-5)):
+            spr.run(maxit, 0.85, tol)
+            out.append((spr.ran_iterations, spr.error, spr.scores_host()))
+        single = g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores() if rank == 0 else None
+        if rank == 0:
+            q.put((spr.exchange, spr.ranges, out, single))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_sharded_page_rank_matches_oracle(exchange):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import oracle
+    scale, world = 16, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scale, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    used, ranges, out, single = q.get()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert used == exchange
+    src, dst = oracle.rmat_edges(scale, seed=42)
+    n = 1 << scale
+    out_off, _ = oracle.csr_build(src, dst, n, oracle.OUTGOING, oracle.SORTED)
+    in_off, in_tgt = oracle.csr_build(src, dst, n, oracle.INCOMING, oracle.SORTED)
+    for (maxit, tol), (it, err, scores) in zip(((20, 0.0), (60, 1e-5)), out):
+        want, wit, werr = oracle.page_rank_jacobi(in_off, in_tgt, out_off, maxit, tol, 0.85, acc64=True)
+        assert it == wit
+        assert np.max(np.abs(scores - want) / want) <= 1e-6
+        assert abs(err - werr) <= 2e-6
+    assert np.max(np.abs(out[0][2] - single) / single) <= 1e-6
