@@ -250,7 +250,7 @@ def run_single(args):
             traffic = json.loads(tp.read_text()).get(f"scale{scale}")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_pr_pull", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_pr_seg + k_pr_sell (one sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": hot_ms / max(hot_n, 1),
                 "kernel_share_of_step": (hot_ms / max(min(args.steps, 3), 1)) / (ms / args.steps)}
@@ -358,7 +358,7 @@ def run_multi(args):
                     "d2h_bytes_per_step": int(4 * n), "steps": e2e_steps,
                     "what": "sharded page_rank on resident shards + all ranks' scores copied to the host"},
             "gpu_launches": int(spr.launches),
-            "roofline": {"bound": "hbm", "kernel": "k_pr_pull", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_pr_seg + k_pr_sell (one sweep)", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs, whole step incl. exchange"},
             "cpu_baseline": None,

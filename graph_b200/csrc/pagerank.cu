@@ -7,15 +7,16 @@
 //            multiply/add (no FMA), IEEE division.  One warp walks the vertices in id order; lanes
 //            only parallelise the gather loads, the additions stay sequential.  Bit-exact with the
 //            reference wherever the reference is deterministic (n <= 16384 = one chunk).
-//   JACOBI — the throughput path.  Vertices are renumbered internally (rows with in-edges first,
-//            then by out-degree descending, so the hot part of the gathered vector is contiguous and
-//            each row's sources are sorted hot-first); the merged sequence "row 0 edges, row 0 end,
-//            row 1 edges, row 1 end, ..." is cut into equal chunks of PR_CHUNK items (merge-path), one
-//            warp per chunk.  A warp streams its slice of the target array with 128-bit loads,
-//            gathers out_scores, stages the values in shared memory and reduces every row that ends
-//            in its chunk; rows that straddle chunks leave a partial sum (carry) that a small fix-up
-//            kernel combines in chunk order, so the result is deterministic.  Vertices without
-//            in-edges are constant after the first sweep and are skipped from then on.
+//   JACOBI — the throughput path (double-buffered, deterministic).  Vertices are renumbered internally
+//            by in-degree descending, then out-degree descending: hub rows come first, rows of equal
+//            length are neighbours, and the most gathered sources sit at the front of out_scores.
+//            Rows with more than 256 in-edges are cut into padded 256-edge SEGMENTS (one warp per
+//            segment: two 128-bit loads of the target stream per lane, 8 gathers, warp-shuffle sum ->
+//            one partial per segment); all other rows live in a SELL-32 layout (32 rows of (almost)
+//            equal length per slice, one lane per row, 128-bit coalesced target loads, no reduction).
+//            Both kernels mirror the first 52 K entries of out_scores in shared memory.  A finish
+//            kernel adds each hub row's partials in segment order and reduces the sweep error in a
+//            fixed order.  Vertices without in-edges are constant after the first sweep and skipped.
 //
 // Algorithmic bytes per sweep: 4m (targets) + 4(n+1) (offsets) + 5*4n (out_scores read+write,
 // scores read+write, out-degree read) = 4m + 24n + 4  (BASELINE.md §3).
@@ -23,59 +24,59 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace gb {
 
-constexpr int PR_CHUNK = 252;      // merge-path items per warp task (edges + PR_ROW_COST per row end)
-constexpr int PR_ROW_COST = 8;     // items charged per row end: a chunk never ends more than 32 rows
-constexpr int PR_SLOTS = 256;      // register slots of a chunk: 8 consecutive edges per lane
-constexpr int PR_WARPS = 32;       // warps per CTA of the sweep kernel: one persistent CTA per SM
+constexpr int PR_WARPS = 32;        // warps per CTA of the sweep kernels: one persistent CTA per SM
 constexpr int PR_THREADS = PR_WARPS * 32;
-constexpr int PR_HOT = 52 * 1024;  // out_scores entries mirrored in shared memory (208 KB)
-constexpr int PR_WARP_SMEM = PR_SLOTS + 36 * 4;  // per warp: 256 head bytes + 36 row sums
-constexpr int PR_FIX_THREADS = 256;
+constexpr int PR_HOT = 32 * 1024;   // out_scores entries mirrored in shared memory (128 KB; L1 keeps ~96 KB)
+constexpr int PR_HOT_MAX = 52 * 1024;  // upper bound of the GB_PR_HOT experiment knob
+constexpr int PR_FIN_THREADS = 256;
+constexpr uint32_t PR_LONG_DEG = 256;  // rows with more in-edges are cut into segments, the rest go to SELL-32
+constexpr uint32_t PR_SEG = 256;       // edges per segment (8 per lane)
 constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;
 
-// the merge-path chunking of a contiguous range of internal rows (the whole graph on one GPU, or
-// one rank's shard of the 1-D edge-cut)
+// the share of a contiguous range of internal rows (the whole graph on one GPU, or one rank's shard
+// of the 1-D edge-cut) in the two layouts
 struct PrRange {
-  uint32_t row_begin = 0, row_end = 0;  // internal rows [row_begin, row_end), clipped to active rows
-  uint64_t item_base = 0;               // off[row_begin] + row_begin
-  uint32_t num_chunks = 0;
-  uint32_t num_fix = 0;
-  unsigned grid_pull = 1, grid_fix = 1;
-  DevBuf<uint2> coord;       // merge-path (row, edge) start of each chunk [num_chunks+1]
-  DevBuf<uint32_t> fix;      // chunks whose first row started in an earlier chunk [num_fix]
-  DevBuf<float> carry_tail;  // per chunk: partial sum of the row continuing into the next chunk
-  DevBuf<float> head_part;   // per chunk: partial sum of a first row continued from earlier chunks
-  DevBuf<double> block_err;  // per CTA error partials (pull CTAs, then fix CTAs)
+  uint32_t row_begin = 0, row_end = 0;    // internal rows [row_begin, row_end), clipped to active rows
+  uint32_t long_begin = 0, long_end = 0;  // hub rows of the range
+  uint32_t seg_begin = 0, seg_end = 0;    // their segments
+  uint32_t slice_begin = 0, slice_end = 0;  // SELL slices of the range
+  uint32_t sell_row_end = 0;                // one past the last SELL row of the range
+  unsigned grid_seg = 0, grid_sell = 0, grid_fin = 1;
+  DevBuf<double> block_err;  // per CTA error partials (SELL CTAs, then finish CTAs)
   DevBuf<double> err_hist;   // error of each sweep of the current batch
   DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
-  uint64_t bytes() const {
-    return coord.bytes() + fix.bytes() + carry_tail.bytes() + head_part.bytes() + block_err.bytes() +
-           err_hist.bytes() + ctrl.bytes();
-  }
+  uint64_t bytes() const { return block_err.bytes() + err_hist.bytes() + ctrl.bytes(); }
 };
 
 struct PrPlan {
   uint32_t n = 0;
   uint32_t n_active = 0;  // rows with in-degree > 0 (renumbered to [0, n_active))
+  uint32_t n_long = 0;    // rows [0, n_long) have more than PR_LONG_DEG in-edges
   uint64_t m = 0;
-  DevBuf<uint32_t> new_id;   // old id -> internal id
-  DevBuf<uint32_t> off;      // internal in-CSR offsets [n+1]
-  DevBuf<uint32_t> tgt;      // internal in-CSR targets [m] (+8 slack)
-  DevBuf<uint32_t> outdeg;   // out-degree by internal id [n]
-  DevBuf<float> x[2];        // out_scores ping-pong [n]
-  DevBuf<float> scores;      // ranks by internal id [n]
-  PrRange all;               // chunking of every active row (single-GPU path)
-  uint32_t hot_count = 0;    // entries of out_scores mirrored in shared memory by the sweep kernel
-  size_t smem_bytes = 0;     // dynamic shared memory of the sweep kernel
+  uint32_t num_segs = 0, num_slices = 0;
+  DevBuf<uint32_t> new_id;    // old id -> internal id
+  DevBuf<uint32_t> off;       // internal in-CSR offsets [n+1] (plan-time and partitioning only)
+  DevBuf<uint32_t> outdeg;    // out-degree by internal id [n]
+  DevBuf<uint32_t> seg_first; // first segment of each hub row [n_long+1]
+  DevBuf<uint4> seg_tgt;      // hub rows' targets, 64 uint4 per segment, tail padded with ~0
+  DevBuf<float> partial;      // one partial sum per segment
+  DevBuf<uint4> sell;         // SELL-32 targets: slice-major, then 4-edge group, then lane
+  DevBuf<uint2> slice_meta;   // per slice: (first uint4 index, uint4 groups per lane)
+  DevBuf<float> x[2];         // out_scores ping-pong [n]
+  DevBuf<float> scores;       // ranks by internal id [n]
+  PrRange all;                // the whole active range (single-GPU path)
+  uint32_t hot_count = 0;     // entries of out_scores mirrored in shared memory by the sweep kernels
+  size_t smem_bytes = 0;      // dynamic shared memory of the sweep kernels
   std::vector<cudaEvent_t> prof_events;
   uint64_t bytes() const {
-    return new_id.bytes() + off.bytes() + tgt.bytes() + outdeg.bytes() + x[0].bytes() + x[1].bytes() +
-           scores.bytes() + all.bytes();
+    return new_id.bytes() + off.bytes() + outdeg.bytes() + seg_first.bytes() + seg_tgt.bytes() + partial.bytes() +
+           sell.bytes() + slice_meta.bytes() + x[0].bytes() + x[1].bytes() + scores.bytes() + all.bytes();
   }
 };
 
@@ -110,18 +111,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// the per-vertex update of page_rank.rs:148-158 with the reference's rounding sequence
-struct PrArgs;
-template <bool PEERS>
-__device__ __forceinline__ double pr_finalize(uint32_t r, float sum, const PrArgs& a);
-
 // ---- plan construction kernels ---------------------------------------------------------------
 __global__ void k_perm_keys(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ out_off,
                             uint32_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     uint32_t indeg = in_off[v + 1] - in_off[v];
     uint32_t outdeg = out_off[v + 1] - out_off[v];
-    keys[v] = ((uint64_t)(indeg == 0) << 32) | (uint32_t)(~outdeg);  // active first, hot first
+    // in-degree descending (rows of similar length become neighbours: SELL slices need no padding and
+    // hub rows come first), then out-degree descending (hot sources first inside equal in-degrees).
+    // R-MAT's expected in- and out-degree of a vertex coincide, so this is also a hot-first order.
+    keys[v] = ((uint64_t)(uint32_t)(~indeg) << 32) | (uint32_t)(~outdeg);
     ids[v] = v;
   }
 }
@@ -161,61 +160,32 @@ __global__ void k_mark_ends_key(const uint64_t* __restrict__ keys, uint64_t coun
     if (i + 1 == count || (uint32_t)(keys[i + 1] >> bits) != r) marks[r + 1] = (uint32_t)(i + 1);
   }
 }
-// merge-path split: chunk k starts at diagonal k*PR_CHUNK of (row ends) x (edges)
-__global__ void k_merge_coords(const uint32_t* __restrict__ off, uint32_t row_begin, uint32_t row_end,
-                               uint64_t item_base, uint64_t items, uint32_t num_chunks,
-                               uint2* __restrict__ coord) {
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= num_chunks; k += gridDim.x * blockDim.x) {
-    uint64_t diag = (uint64_t)k * PR_CHUNK;
-    if (diag > items) diag = items;
-    diag += item_base;  // absolute position in the merged sequence: row r's edges, then PR_ROW_COST slots
-    // r0 = first row whose end marker (first slot at off[r+1] + COST*r) is not before the diagonal
-    uint32_t lo = row_begin, hi = row_end;
-    while (lo < hi) {
-      uint32_t mid = lo + (hi - lo) / 2;
-      if ((uint64_t)off[mid + 1] + (uint64_t)PR_ROW_COST * mid < diag) lo = mid + 1; else hi = mid;
-    }
-    // edges before the diagonal: all edges of rows < r0 plus the part of row r0 in front of it
-    uint32_t e;
-    if (lo >= row_end) {
-      e = off[row_end];
-    } else {
-      const int64_t want = (int64_t)diag - (int64_t)PR_ROW_COST * lo;
-      const int64_t b = off[lo], t = off[lo + 1];
-      e = (uint32_t)(want < b ? b : (want > t ? t : want));
-    }
-    coord[k] = make_uint2(lo, e);
-  }
-}
-__global__ void k_fix_flags(const uint32_t* __restrict__ off, const uint2* __restrict__ coord,
-                            uint32_t num_chunks, uint8_t* __restrict__ flags) {
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < num_chunks; k += gridDim.x * blockDim.x) {
-    uint2 c0 = coord[k], c1 = coord[k + 1];
-    flags[k] = (c0.x < c1.x && off[c0.x] < c0.y) ? 1 : 0;
-  }
-}
-
 // ---- sweep kernels (JACOBI) ------------------------------------------------------------------
 struct PrArgs {
-  const uint32_t* off;
-  const uint32_t* tgt;
   const uint32_t* outdeg;
-  const uint2* coord;
-  const uint32_t* fix;
   const float* x_cur;
   float* x_next;
   float* peer_next[7];  // peer-mapped copies of x_next (fused allgather over NVLink); n_peers used
   uint32_t n_peers;
   uint32_t hot_count;   // entries of x_cur mirrored in shared memory (multiple of 4)
-  uint64_t item_base;
   float* scores;
-  float* carry_tail;
-  float* head_part;
+  // hub rows
+  const uint4* seg_tgt;
+  const uint32_t* seg_first;
+  float* partial;
+  uint32_t seg_begin, seg_end;
+  uint32_t long_begin, long_end;
+  // SELL rows
+  const uint4* sell;
+  const uint2* slice_meta;
+  uint32_t slice_begin, slice_end;
+  uint32_t sell_row0;     // row of lane 0 of slice 0 (= n_long)
+  uint32_t sell_row_end;  // one past the last SELL row of this range
+  // error / stop rule
   double* block_err;
   double* err_hist;
   uint32_t* ctrl;
-  uint32_t row_end, num_chunks, num_fix;  // row_end: one past the last row of this range
-  unsigned grid_pull;
+  uint32_t err_base_fin;  // block_err slots [0, err_base_fin) belong to the SELL CTAs
   float base, damping;
   double tolerance;
   double extra_err;   // closed-form error of the skipped zero-in-degree rows (first sweep only)
@@ -223,12 +193,51 @@ struct PrArgs {
   uint32_t sweep_no;  // 1-based global sweep number
 };
 
+// 8 gathers per lane in straight-line predicated code: ids below hot_n read the shared-memory mirror,
+// all others (except the padding id ~0) read global memory through L1 (ld.global.nc).  Measured
+// (profiles/r01_sweep_hot_head.txt): per-target if/else made every load wait for a scoreboard slot of
+// the previous one; and every pending miss holds an L1 line, so the hot head must leave L1 room —
+// at 208 KB of shared memory (16 KB of L1) the sweep ran 2.8x slower than at 128 KB (96 KB of L1);
+// ld.global.nc.L1::no_allocate was slower still at every size.
+__device__ __forceinline__ void pr_gather(const float* x, uint32_t hot_saddr, uint32_t hot_n,
+                                          const uint4& ta, const uint4& tb, float (&v)[8]) {
+  const uint32_t t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+  float vs[8], vg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.lt.u32 p, %1, %2;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.shared.f32 %0, [%3];\n\t}"
+        : "=f"(vs[j])
+        : "r"(t[j]), "r"(hot_n), "r"(hot_saddr + 4u * t[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ge.u32 p, %1, %2;\n\t"
+        "setp.ne.and.u32 p, %1, 0xffffffff, p;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.global.nc.f32 %0, [%3];\n\t}"
+        : "=f"(vg[j])
+        : "r"(t[j]), "r"(hot_n), "l"(x + t[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = vs[j] + vg[j];
+}
+__device__ __forceinline__ float pr_sum8(const float (&v)[8]) {
+  return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+}
+__device__ __forceinline__ uint4 pr_ld4(const uint4* p) { return ld_stream_u4(reinterpret_cast<const uint32_t*>(p)); }
+
+// the per-vertex update of page_rank.rs:148-158 with the reference's rounding sequence
 template <bool PEERS>
-__device__ __forceinline__ double pr_finalize(uint32_t r, float sum, const PrArgs& a) {
-  const float old = a.scores[r];
+__device__ __forceinline__ double pr_update(uint32_t r, float sum, float old, uint32_t deg, const PrArgs& a) {
   const float nw = __fadd_rn(a.base, __fmul_rn(a.damping, sum));
   a.scores[r] = nw;
-  const float xo = __fdiv_rn(nw, (float)a.outdeg[r]);
+  const float xo = __fdiv_rn(nw, (float)deg);
   a.x_next[r] = xo;
   // fused allgather: the finished out_score also goes straight into every peer's next vector
   if (PEERS)
@@ -236,227 +245,127 @@ __device__ __forceinline__ double pr_finalize(uint32_t r, float sum, const PrArg
   return fabs((double)__fsub_rn(nw, old));
 }
 
-// The sweep: one persistent CTA per SM.  The first PR_HOT entries of out_scores — the most gathered
-// sources, contiguous thanks to the out-degree ordering — are mirrored in shared memory once per
-// sweep; gathers of those ids are shared-memory loads (bank-limited, ~10 per clock per SM) instead
-// of divergent global loads (L1TEX accepts ~0.57 sectors per clock per SM: the measured ceiling of
-// the first version of this kernel).  Targets are read with lane-consecutive 32-bit loads so that
-// one gather instruction covers 32 consecutive entries of a sorted row and coalesces wherever a
-// row's sources are dense.
-struct RowMeta {
-  uint32_t os, oe, deg;
-  float old;
-};
-// offsets / out-degree / old score of the rows ending in a chunk (one row per lane, at most 32)
-__device__ __forceinline__ RowMeta pr_load_meta(const PrArgs& a, uint32_t r0, uint32_t r1, uint32_t lane) {
-  RowMeta m{0u, 0u, 1u, 0.0f};
-  const uint32_t r = r0 + lane;
-  if (r < r1) {
-    m.os = a.off[r];
-    m.oe = a.off[r + 1];
-    m.deg = a.outdeg[r];
-    m.old = a.scores[r];
-  }
-  return m;
-}
-// 8 consecutive targets per lane (two aligned 128-bit loads); slots outside [e0, e1) become ~0
-__device__ __forceinline__ void pr_load_targets(const uint32_t* __restrict__ tgt, uint32_t e0, uint32_t e1,
-                                                uint32_t lane, uint32_t (&t)[8]) {
-  const uint32_t i0 = (e0 & ~3u) + 8 * lane;
-  uint4 ta = make_uint4(~0u, ~0u, ~0u, ~0u), tb = ta;
-  if (i0 < e1) ta = ld_stream_u4(tgt + i0);
-  if (i0 + 4 < e1) tb = ld_stream_u4(tgt + i0 + 4);
-  t[0] = ta.x; t[1] = ta.y; t[2] = ta.z; t[3] = ta.w;
-  t[4] = tb.x; t[5] = tb.y; t[6] = tb.z; t[7] = tb.w;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (i0 + j < e0 || i0 + j >= e1) t[j] = ~0u;
-}
-__device__ __forceinline__ void pr_gather(const float* __restrict__ x, const float* hot, uint32_t hot_n,
-                                          const uint32_t (&t)[8], float (&v)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t tj = t[j];
-    float val = 0.0f;
-    if (tj < hot_n) val = hot[tj];
-    else if (tj != ~0u) val = __ldg(x + tj);
-    v[j] = val;
-  }
-}
-
-template <bool PEERS>
-__device__ __forceinline__ double pr_update(uint32_t r, float sum, float old, uint32_t deg, const PrArgs& a) {
-  const float nw = __fadd_rn(a.base, __fmul_rn(a.damping, sum));
-  a.scores[r] = nw;
-  const float xo = __fdiv_rn(nw, (float)deg);
-  a.x_next[r] = xo;
-  if (PEERS)
-    for (uint32_t p = 0; p < a.n_peers; ++p) a.peer_next[p][r] = xo;
-  return fabs((double)__fsub_rn(nw, old));
-}
-
-// The sweep: one persistent CTA per SM.
-//  * The first PR_HOT entries of out_scores — the most gathered sources, contiguous thanks to the
-//    out-degree ordering — are mirrored in shared memory once per sweep; gathers of those ids are
-//    shared-memory loads instead of divergent global loads (L1TEX accepts only ~0.57 divergent
-//    sectors per clock per SM: the measured ceiling of the first version of this kernel).
-//  * A chunk is <= 252 consecutive edges and <= 32 row ends.  Each lane owns 8 consecutive edges
-//    (two 128-bit loads of the target stream), gathers them into registers, sums its own run
-//    between row boundaries and one warp-level segmented scan joins the runs across lanes; the row
-//    totals meet their rows (one lane per row, metadata prefetched) through 33 floats of smem.
-//  * Two-deep software pipeline: while chunk k is reduced, the gathers of chunk k+1, the targets of
-//    chunk k+2 and the coordinates of chunk k+3 are already in flight.
-template <bool PEERS>
-__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_pull(const PrArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* hot = smem;  // [hot_count]
-  unsigned char* warp_base = reinterpret_cast<unsigned char*>(smem + a.hot_count);
-  __shared__ double warp_err[PR_WARPS];
-  if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* heads = warp_base + warp * PR_WARP_SMEM;            // [256] row id + 1 at the slot a row starts
-  float* rs = reinterpret_cast<float*>(heads + PR_SLOTS);            // [36] row totals of this chunk
-  const float* __restrict__ x = a.x_cur;
-  const uint32_t hot_n = a.hot_count;
+__device__ __forceinline__ void pr_load_hot(float* hot, const float* __restrict__ x, uint32_t hot_n) {
   for (uint32_t i = threadIdx.x * 4; i < hot_n; i += PR_THREADS * 4)
     *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
   __syncthreads();
-  double err = 0.0;
+}
 
+// ---- hub rows: 256-edge segments, 32 segments per slice, one lane per segment ----------------------
+// Divergent 4-byte gathers sustain ~0.95 per clock per SM on B200 whatever the load path
+// (profiles/r01_gather_ceiling_microbench.txt), so everything around the gathers is kept minimal.  A
+// slice interleaves 32 segments group-major / lane-minor exactly like a SELL slice of width 64: every
+// lane streams its own segment with 128-bit coalesced loads and keeps a private sum — there is no
+// cross-lane reduction (the shuffle tree of a warp-per-segment version cost a third of its time).
+__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_seg(const PrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* hot = smem;
+  if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* x = a.x_cur;
+  const uint32_t hot_n = a.hot_count;
+  pr_load_hot(hot, x, hot_n);
+  const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
   const uint32_t stride = gridDim.x * PR_WARPS;
-  const uint32_t K = a.num_chunks;
-  uint32_t k = blockIdx.x * PR_WARPS + warp;
-  uint2 c0 = make_uint2(0, 0), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
-  uint32_t t[8];
-  float v[8];
-  RowMeta cur{0u, 0u, 1u, 0.0f}, nxt = cur;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    t[j] = ~0u;
-    v[j] = 0.0f;
+  const uint32_t slice_end = (a.seg_end + 31) / 32;
+  constexpr uint32_t W4 = PR_SEG / 4;  // uint4 groups per segment
+  for (uint32_t sl = a.seg_begin / 32 + blockIdx.x * PR_WARPS + warp; sl < slice_end; sl += stride) {
+    const uint4* base = a.seg_tgt + (size_t)sl * (W4 * 32) + lane;
+    uint4 ta = pr_ld4(base), tb = pr_ld4(base + 32);
+    float acc = 0.0f;
+#pragma unroll 2
+    for (uint32_t q = 0; q < W4; q += 2) {
+      const uint4 na = (q + 2 < W4) ? pr_ld4(base + (q + 2) * 32) : ta;
+      const uint4 nb = (q + 3 < W4) ? pr_ld4(base + (q + 3) * 32) : tb;
+      float v[8];
+      pr_gather(x, hot_saddr, hot_n, ta, tb, v);
+      acc += pr_sum8(v);
+      ta = na;
+      tb = nb;
+    }
+    const uint32_t seg = sl * 32 + lane;
+    if (seg >= a.seg_begin && seg < a.seg_end) a.partial[seg] = acc;
   }
-  if (k < K) {
-    c0 = a.coord[k];
-    c1 = a.coord[k + 1];
-    if (k + stride < K) {
-      n0 = a.coord[k + stride];
-      n1 = a.coord[k + stride + 1];
+}
+
+// ---- SELL-32 sweep for rows with at most PR_LONG_DEG in-edges -------------------------------------
+// Rows are sorted by in-degree, so the 32 rows of a slice have (almost) the same length: one lane per
+// row, no reduction, no per-row offsets.  A lane reads its row four targets at a time (128-bit,
+// coalesced: the slice is stored group-major, lane-minor), gathers, and adds in row order.  The next
+// slice's first targets and row metadata are requested while the current slice is processed.
+template <bool PEERS>
+__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* hot = smem;
+  __shared__ double warp_err[PR_WARPS];
+  if (a.ctrl[0] != 0) return;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ x = a.x_cur;
+  const uint32_t hot_n = a.hot_count;
+  pr_load_hot(hot, x, hot_n);
+  const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
+  double err = 0.0;
+  const uint32_t stride = gridDim.x * PR_WARPS;
+  const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
+  uint32_t sidx = a.slice_begin + blockIdx.x * PR_WARPS + warp;
+  // pipeline state: metadata of this and the next slice, first two target groups + row data of this one
+  uint2 meta = make_uint2(0, 0), nmeta = meta;
+  uint4 ta = pad, tb = pad;
+  float old = 0.0f;
+  uint32_t deg = 1;
+  if (sidx < a.slice_end) {
+    meta = __ldg(a.slice_meta + sidx);
+    if (sidx + stride < a.slice_end) nmeta = __ldg(a.slice_meta + sidx + stride);
+    const uint4* base = a.sell + meta.x + lane;
+    if (0 < meta.y) ta = pr_ld4(base);
+    if (1 < meta.y) tb = pr_ld4(base + 32);
+    const uint32_t row = a.sell_row0 + 32 * sidx + lane;
+    if (row < a.sell_row_end) {
+      old = a.scores[row];
+      deg = a.outdeg[row];
     }
-    if (k + 2 * stride < K) {
-      m0 = a.coord[k + 2 * stride];
-      m1 = a.coord[k + 2 * stride + 1];
-    }
-    pr_load_targets(a.tgt, c0.y, c1.y, lane, t);
-    cur = pr_load_meta(a, c0.x, c1.x, lane);
-    pr_gather(x, hot, hot_n, t, v);
-    if (k + stride < K) pr_load_targets(a.tgt, n0.y, n1.y, lane, t);
   }
-  while (k < K) {
-    const uint32_t r0 = c0.x, e0 = c0.y, r1 = c1.x, e1 = c1.y;
-    const uint32_t a0 = e0 & ~3u;
-    const uint32_t nr = r1 - r0;  // rows ending in this chunk (<= 32)
-    const uint32_t kn = k + stride, knn = kn + stride;
-
-    // ---- heads: where does each row of this chunk start among the 256 slots? -----------------
-    uint32_t seg_s = 0, seg_e = 0;
-    bool tail_exists = false;
-    if (nr) {
-      *reinterpret_cast<uint2*>(heads + 8 * lane) = make_uint2(0u, 0u);
-      __syncwarp();
-      if (lane < nr) {
-        seg_s = cur.os > e0 ? cur.os : e0;
-        seg_e = cur.oe;
-        if (seg_e > seg_s) heads[seg_s - a0] = (unsigned char)(lane + 1);
+  while (sidx < a.slice_end) {
+    const uint32_t w4 = meta.y;
+    const uint4* base = a.sell + meta.x + lane;
+    const uint32_t row = a.sell_row0 + 32 * sidx + lane;
+    // next slice: first groups, row data; metadata of the slice after it
+    const uint32_t nidx = sidx + stride;
+    uint4 nta = pad, ntb = pad;
+    float nold = 0.0f;
+    uint32_t ndeg = 1;
+    uint2 nnmeta = make_uint2(0, 0);
+    if (nidx < a.slice_end) {
+      const uint4* nbase = a.sell + nmeta.x + lane;
+      if (0 < nmeta.y) nta = pr_ld4(nbase);
+      if (1 < nmeta.y) ntb = pr_ld4(nbase + 32);
+      const uint32_t nrow = a.sell_row0 + 32 * nidx + lane;
+      if (nrow < a.sell_row_end) {
+        nold = a.scores[nrow];
+        ndeg = a.outdeg[nrow];
       }
-      // the row that continues into the next chunk starts where the last ending row stops
-      const uint32_t last_oe = __shfl_sync(0xFFFFFFFFu, cur.oe, nr - 1);
-      tail_exists = last_oe < e1;
-      if (lane == 0 && tail_exists) heads[last_oe - a0] = (unsigned char)(nr + 1);
-      __syncwarp();
+      if (nidx + stride < a.slice_end) nnmeta = __ldg(a.slice_meta + nidx + stride);
     }
-
-    // ---- lane-local runs between row starts -----------------------------------------------------
-    float run = 0.0f, head_sum = 0.0f;
-    uint32_t first_f = 0, prev_f = 0;
-    if (nr) {
-      const uint2 hb = *reinterpret_cast<const uint2*>(heads + 8 * lane);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t f = ((j < 4 ? hb.x : hb.y) >> (8 * (j & 3))) & 0xFFu;
-        if (f) {
-          if (prev_f == 0) {
-            head_sum = run;  // belongs to the run entering this lane
-            first_f = f;
-          } else {
-            rs[prev_f - 1] = run;  // a row that starts and ends inside this lane
-          }
-          prev_f = f;
-          run = 0.0f;
-        }
-        run += v[j];
-      }
-    } else {
-      run = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    float acc = 0.0f;
+    for (uint32_t q = 0; q < w4; q += 2) {
+      // targets of the next two groups are requested before this group's gathers are consumed
+      const uint4 na = (q + 2 < w4) ? pr_ld4(base + (q + 2) * 32) : pad;
+      const uint4 nb = (q + 3 < w4) ? pr_ld4(base + (q + 3) * 32) : pad;
+      float v[8];
+      pr_gather(x, hot_saddr, hot_n, ta, tb, v);
+      acc += pr_sum8(v);
+      ta = na;
+      tb = nb;
     }
-
-    // ---- v is consumed: issue the next chunk's gathers and the loads behind them ---------------
-    uint2 q0 = make_uint2(0, 0), q1 = q0;
-    if (kn < K) {
-      pr_gather(x, hot, hot_n, t, v);
-      nxt = pr_load_meta(a, n0.x, n1.x, lane);
-      if (knn < K) {
-        pr_load_targets(a.tgt, m0.y, m1.y, lane, t);
-        if (knn + stride < K) {
-          q0 = a.coord[knn + stride];
-          q1 = a.coord[knn + stride + 1];
-        }
-      }
-    }
-
-    if (nr == 0) {
-      // the whole chunk lies inside one (long) row
-      const float acc = warp_sum(run);
-      if (lane == 0) a.carry_tail[k] = acc;
-    } else {
-      // ---- segmented inclusive scan of the lane runs (a lane with a row start blocks the carry) --
-      const unsigned flagged = __ballot_sync(0xFFFFFFFFu, prev_f != 0);
-      float val = run;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float up = __shfl_up_sync(0xFFFFFFFFu, val, d);
-        // lanes (lane-d, lane] must hold no row start for the carry to pass
-        const unsigned window = (lane >= (uint32_t)d) ? ((flagged >> (lane - d + 1)) & ((1u << d) - 1u)) : 1u;
-        if (window == 0) val += up;
-      }
-      float carry_in = __shfl_up_sync(0xFFFFFFFFu, val, 1);
-      if (lane == 0) carry_in = 0.0f;
-      // the run that entered this lane ends at its first row start: it is row first_f - 2
-      if (first_f >= 2) rs[first_f - 2] = carry_in + head_sum;
-      // the last run of the chunk: total sits in lane 31, its row id in the last flagged lane
-      const int last_lane = 31 - __clz(flagged);  // flagged != 0: row 0 or row 1 starts in this chunk
-      const uint32_t last_f = __shfl_sync(0xFFFFFFFFu, prev_f, last_lane);
-      if (lane == 31 && last_f) rs[last_f - 1] = val;
-      __syncwarp();
-      // ---- one lane per row: finish it ----------------------------------------------------------
-      if (lane < nr) {
-        const float sum = (seg_e > seg_s) ? rs[lane] : 0.0f;
-        if (cur.os < e0) a.head_part[k] = sum;  // row began in an earlier chunk: fix-up kernel finishes it
-        else err += pr_update<PEERS>(r0 + lane, sum, cur.old, cur.deg, a);
-      }
-      if (lane == 0) a.carry_tail[k] = tail_exists ? rs[nr] : 0.0f;
-      __syncwarp();
-    }
-
-    k = kn;
-    c0 = n0;
-    c1 = n1;
-    n0 = m0;
-    n1 = m1;
-    m0 = q0;
-    m1 = q1;
-    cur = nxt;
+    if (row < a.sell_row_end) err += pr_update<PEERS>(row, acc, old, deg, a);
+    sidx = nidx;
+    meta = nmeta;
+    nmeta = nnmeta;
+    ta = nta;
+    tb = ntb;
+    old = nold;
+    deg = ndeg;
   }
-
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
   __syncthreads();
@@ -468,45 +377,30 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_pull(const PrArgs a) {
   }
 }
 
-// combines the partial sums of rows that straddle chunks (one warp per such row) and, in the last
-// CTA to finish, reduces the error of the sweep in a fixed order and evaluates the stop rule of
-// page_rank.rs:107.
+// ---- finish: hub rows = sum of their segment partials (fixed order), then the sweep error ---------
+// One warp per hub row; the last CTA to finish reduces all CTA error partials in a fixed order and
+// evaluates the stop rule of page_rank.rs:107 on the device.
 template <bool PEERS>
-__global__ void __launch_bounds__(PR_FIX_THREADS) k_pr_fix(const PrArgs a) {
-  constexpr int FIX_WARPS = PR_FIX_THREADS / 32;
-  __shared__ double warp_err[FIX_WARPS];
+__global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
+  constexpr int FIN_WARPS = PR_FIN_THREADS / 32;
+  __shared__ double warp_err[FIN_WARPS];
   __shared__ bool is_last;
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double err = 0.0;
-  const uint32_t nthreads = gridDim.x * PR_FIX_THREADS;
-  // one lane per straddling row; rows spanning many chunks (hubs) are summed by the whole warp
-  for (uint32_t ib = blockIdx.x * PR_FIX_THREADS + warp * 32; ib < a.num_fix; ib += nthreads) {
-    const uint32_t i = ib + lane;
-    const bool live = i < a.num_fix;
-    uint32_t k = 0, r0 = 0, j0 = 0;
-    if (live) {
-      k = a.fix[i];
-      r0 = a.coord[k].x;
-      j0 = (uint32_t)(((uint64_t)a.off[r0] + (uint64_t)PR_ROW_COST * r0 - a.item_base) / PR_CHUNK);  // chunk holding the row's first edge
+  const uint32_t nwarps = gridDim.x * FIN_WARPS;
+  for (uint32_t r = a.long_begin + blockIdx.x * FIN_WARPS + warp; r < a.long_end; r += nwarps) {
+    const uint32_t sb = a.seg_first[r], se = a.seg_first[r + 1];
+    float old = 0.0f;
+    uint32_t deg = 1;
+    if (lane == 0) {
+      old = a.scores[r];
+      deg = a.outdeg[r];
     }
-    const uint32_t span = k - j0;
-    const bool is_long = live && span > 8;
     float p = 0.0f;
-    if (live && !is_long)
-      for (uint32_t j = j0; j < k; ++j) p += a.carry_tail[j];
-    unsigned long_mask = __ballot_sync(0xFFFFFFFFu, is_long);
-    while (long_mask) {
-      const int owner = __ffs(long_mask) - 1;
-      long_mask &= long_mask - 1;
-      const uint32_t oj = __shfl_sync(0xFFFFFFFFu, j0, owner);
-      const uint32_t ok = __shfl_sync(0xFFFFFFFFu, k, owner);
-      float q = 0.0f;
-      for (uint32_t j = oj + lane; j < ok; j += 32) q += a.carry_tail[j];
-      q = warp_sum(q);
-      if ((int)lane == owner) p = q;
-    }
-    if (live) err += pr_finalize<PEERS>(r0, p + a.head_part[k], a);
+    for (uint32_t j = sb + lane; j < se; j += 32) p += a.partial[j];
+    p = warp_sum(p);
+    if (lane == 0) err += pr_update<PEERS>(r, p, old, deg, a);
   }
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
@@ -514,8 +408,8 @@ __global__ void __launch_bounds__(PR_FIX_THREADS) k_pr_fix(const PrArgs a) {
   if (threadIdx.x == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < FIX_WARPS; ++w) t += warp_err[w];
-    a.block_err[a.grid_pull + blockIdx.x] = t;
+    for (int w = 0; w < FIN_WARPS; ++w) t += warp_err[w];
+    a.block_err[a.err_base_fin + blockIdx.x] = t;
     __threadfence();
     unsigned ticket = atomicAdd(&a.ctrl[1], 1u);
     is_last = (ticket == gridDim.x - 1);
@@ -524,19 +418,95 @@ __global__ void __launch_bounds__(PR_FIX_THREADS) k_pr_fix(const PrArgs a) {
   if (!is_last) return;
   __threadfence();
   // fixed-order reduction of all CTA partials (deterministic error)
-  const uint32_t total = a.grid_pull + gridDim.x;
+  const uint32_t total = a.err_base_fin + gridDim.x;
   double t = 0.0;
-  for (uint32_t i = threadIdx.x; i < total; i += PR_FIX_THREADS) t += ((volatile double*)a.block_err)[i];
+  for (uint32_t i = threadIdx.x; i < total; i += PR_FIN_THREADS) t += ((volatile double*)a.block_err)[i];
   t = warp_sum(t);
   if (lane == 0) warp_err[warp] = t;
   __syncthreads();
   if (threadIdx.x == 0) {
     double e = a.extra_err;
 #pragma unroll
-    for (int w = 0; w < FIX_WARPS; ++w) e += warp_err[w];
+    for (int w = 0; w < FIN_WARPS; ++w) e += warp_err[w];
     a.err_hist[a.sweep] = e;
     a.ctrl[1] = 0;
     if (e < a.tolerance) a.ctrl[0] = a.sweep_no;
+  }
+}
+
+// ---- plan-time helpers of the two layouts ---------------------------------------------------------
+__global__ void k_count_rows(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ counts) {
+  uint32_t act = 0, lng = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const uint32_t d = off[r + 1] - off[r];
+    act += d > 0;
+    lng += d > PR_LONG_DEG;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    act += __shfl_xor_sync(0xFFFFFFFFu, act, o);
+    lng += __shfl_xor_sync(0xFFFFFFFFu, lng, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (act) atomicAdd(counts + 0, act);
+    if (lng) atomicAdd(counts + 1, lng);
+  }
+}
+__global__ void k_seg_counts(const uint32_t* __restrict__ off, uint32_t n_long, uint32_t* __restrict__ cnt) {
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_long; r += gridDim.x * blockDim.x)
+    cnt[r] = (r < n_long) ? (off[r + 1] - off[r] + PR_SEG - 1) / PR_SEG : 0;
+}
+// one warp per hub row: copy its targets into its padded segments (slice-interleaved layout:
+// segment s lives in slice s/32 as lane s%32; element j of it is component j%4 of group j/4)
+__global__ void k_seg_fill(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt,
+                           const uint32_t* __restrict__ seg_first, uint32_t n_long, uint32_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = warp; r < n_long; r += nwarps) {
+    const uint32_t b = off[r], d = off[r + 1] - b;
+    const uint32_t s0 = seg_first[r];
+    for (uint32_t j = lane; j < d; j += 32) {
+      const uint32_t sg = s0 + j / PR_SEG, e = j % PR_SEG;
+      const uint64_t idx = (((uint64_t)(sg / 32) * (PR_SEG / 4) + e / 4) * 32 + (sg % 32)) * 4 + (e % 4);
+      out[idx] = tgt[b + j];
+    }
+  }
+}
+__global__ void k_sell_widths(const uint32_t* __restrict__ off, uint32_t row0, uint32_t num_slices,
+                              uint32_t* __restrict__ units) {
+  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x) {
+    const uint32_t r = row0 + 32 * sidx;  // rows are sorted by degree: the first row of a slice is its longest
+    units[sidx] = ((off[r + 1] - off[r] + 3) / 4) * 32;  // uint4 entries of the slice
+  }
+}
+__global__ void k_sell_meta(const uint32_t* __restrict__ units, const uint32_t* __restrict__ bases,
+                            uint32_t num_slices, uint2* __restrict__ meta) {
+  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x)
+    meta[sidx] = make_uint2(bases[sidx], units[sidx] / 32);
+}
+__global__ void k_sell_fill(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t row0,
+                            uint32_t row_end, uint32_t num_slices, const uint2* __restrict__ meta,
+                            uint4* __restrict__ sell) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t sidx = warp; sidx < num_slices; sidx += nwarps) {
+    const uint2 m = meta[sidx];
+    const uint32_t row = row0 + 32 * sidx + lane;
+    uint32_t b = 0, d = 0;
+    if (row < row_end) {
+      b = off[row];
+      d = off[row + 1] - b;
+    }
+    for (uint32_t q = 0; q < m.y; ++q) {
+      uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+      const uint32_t j = 4 * q;
+      if (j + 0 < d) v.x = tgt[b + j + 0];
+      if (j + 1 < d) v.y = tgt[b + j + 1];
+      if (j + 2 < d) v.z = tgt[b + j + 2];
+      if (j + 3 < d) v.w = tgt[b + j + 3];
+      sell[m.x + q * 32 + lane] = v;
+    }
   }
 }
 
@@ -624,44 +594,36 @@ static gb_status build_range(const gb_graph* g, const PrPlan* p, uint32_t row_be
   if (row_begin > row_end) row_begin = row_end;
   r->row_begin = row_begin;
   r->row_end = row_end;
-  uint32_t h_off[2] = {0, 0};
-  GB_CUDA(cudaMemcpyAsync(&h_off[0], p->off.p + row_begin, 4, cudaMemcpyDeviceToHost, s));
-  GB_CUDA(cudaMemcpyAsync(&h_off[1], p->off.p + row_end, 4, cudaMemcpyDeviceToHost, s));
-  GB_CUDA(cudaStreamSynchronize(s));
-  r->item_base = (uint64_t)h_off[0] + (uint64_t)PR_ROW_COST * row_begin;
-  const uint64_t items = (uint64_t)(h_off[1] - h_off[0]) + (uint64_t)PR_ROW_COST * (row_end - row_begin);
-  const uint64_t nchunks = (items + PR_CHUNK - 1) / PR_CHUNK;
-  GB_REQUIRE(nchunks < 0xFFFFFFF0ull, "too many chunks");
-  r->num_chunks = (uint32_t)nchunks;
-  GB_TRY(r->coord.alloc((size_t)r->num_chunks + 1));
-  k_merge_coords<<<grid_for((uint64_t)r->num_chunks + 1, 256), 256, 0, s>>>(
-      p->off.p, row_begin, row_end, r->item_base, items, r->num_chunks, r->coord.p);
-  GB_TRY(r->carry_tail.alloc(std::max<size_t>(r->num_chunks, 1)));
-  GB_TRY(r->head_part.alloc(std::max<size_t>(r->num_chunks, 1)));
-  r->num_fix = 0;
-  GB_TRY(r->fix.alloc(std::max<size_t>(r->num_chunks, 1)));
-  if (r->num_chunks) {
-    DevBuf<uint8_t> flags;
-    DevBuf<uint32_t> d_num;
-    GB_TRY(flags.alloc(r->num_chunks));
-    GB_TRY(d_num.alloc(1));
-    k_fix_flags<<<grid_for(r->num_chunks, 256), 256, 0, s>>>(p->off.p, r->coord.p, r->num_chunks, flags.p);
-    thrust::counting_iterator<uint32_t> iota(0);
-    size_t tb = 0;
-    GB_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, iota, flags.p, r->fix.p, d_num.p, (int)r->num_chunks, s));
-    DevBuf<uint8_t> tmp;
-    GB_TRY(tmp.alloc(tb));
-    GB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, iota, flags.p, r->fix.p, d_num.p, (int)r->num_chunks, s));
-    GB_CUDA(cudaMemcpyAsync(&r->num_fix, d_num.p, 4, cudaMemcpyDeviceToHost, s));
+  // SELL part: rows [max(row_begin, n_long), row_end) — shard boundaries sit on slice boundaries
+  const uint32_t sb = std::max(row_begin, p->n_long), se = std::max(row_end, p->n_long);
+  GB_REQUIRE((sb - p->n_long) % 32 == 0, "shard boundary %u is not on a SELL slice boundary", row_begin);
+  r->slice_begin = (sb - p->n_long) / 32;
+  r->slice_end = (se - p->n_long + 31) / 32;
+  r->sell_row_end = se;
+  // hub rows of the range and their segments
+  r->long_begin = std::min(row_begin, p->n_long);
+  r->long_end = std::min(row_end, p->n_long);
+  r->seg_begin = r->seg_end = 0;
+  if (p->n_long) {
+    uint32_t h[2] = {0, 0};
+    GB_CUDA(cudaMemcpyAsync(&h[0], p->seg_first.p + r->long_begin, 4, cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaMemcpyAsync(&h[1], p->seg_first.p + r->long_end, 4, cudaMemcpyDeviceToHost, s));
     GB_CUDA(cudaStreamSynchronize(s));
+    r->seg_begin = h[0];
+    r->seg_end = h[1];
   }
   int dev_sms = 148;
   GB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
-  const uint64_t want = ((uint64_t)r->num_chunks + PR_WARPS - 1) / PR_WARPS;
-  r->grid_pull = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)dev_sms));  // 1 CTA / SM
-  const uint64_t want_fix = ((uint64_t)r->num_fix + PR_FIX_THREADS - 1) / PR_FIX_THREADS;
-  r->grid_fix = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fix, (uint64_t)dev_sms * 8));
-  GB_TRY(r->block_err.alloc((size_t)r->grid_pull + r->grid_fix));
+  const uint64_t seg_slices = r->seg_end > r->seg_begin ? (r->seg_end + 31) / 32 - r->seg_begin / 32 : 0;
+  const uint64_t want_seg = (seg_slices + PR_WARPS - 1) / PR_WARPS;
+  r->grid_seg = (unsigned)std::min<uint64_t>(want_seg, (uint64_t)dev_sms);  // one persistent CTA per SM
+  const uint64_t want_sell = ((uint64_t)(r->slice_end - r->slice_begin) + PR_WARPS - 1) / PR_WARPS;
+  r->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms);
+  const uint64_t want_fin = ((uint64_t)(r->long_end - r->long_begin) + (PR_FIN_THREADS / 32) - 1) / (PR_FIN_THREADS / 32);
+  r->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
+  const size_t nerr = (size_t)r->grid_sell + r->grid_fin;
+  GB_TRY(r->block_err.alloc(nerr));
+  GB_CUDA(cudaMemsetAsync(r->block_err.p, 0, nerr * sizeof(double), s));
   GB_TRY(r->err_hist.alloc(64));
   GB_TRY(r->ctrl.alloc(2));
   GB_CUDA(cudaMemsetAsync(r->ctrl.p, 0, 8, s));
@@ -693,10 +655,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       cub::DoubleBuffer<uint64_t> kb(keys.p, keys_alt.p);
       cub::DoubleBuffer<uint32_t> vb(ids.p, ids_alt.p);
       size_t tb = 0;
-      GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int)n, 0, 33, s));
+      GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (int)n, 0, 64, s));
       DevBuf<uint8_t> tmp;
       GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int)n, 0, 33, s));
+      GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int)n, 0, 64, s));
       GB_TRY(p->new_id.alloc(n));
       GB_TRY(p->outdeg.alloc(n));
       k_perm_scatter<<<grid_for(n, 256), 256, 0, s>>>(vb.Current(), g->out.off.p, n, p->new_id.p,
@@ -705,10 +667,11 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       GB_CUDA(cudaStreamSynchronize(s));
     }
     // 2. renumbered in-CSR (rows sorted by internal source id: hot sources first)
+    DevBuf<uint32_t> tgt;  // renumbered in-CSR targets: plan-time only, re-laid out below
     GB_TRY(p->off.alloc((size_t)n + 1));
-    GB_TRY(p->tgt.alloc(m, 8));
+    GB_TRY(tgt.alloc(m, 8));
     GB_CUDA(cudaMemsetAsync(p->off.p, 0, ((size_t)n + 1) * 4, s));
-    GB_CUDA(cudaMemsetAsync(p->tgt.p + m, 0, 8 * 4, s));
+    GB_CUDA(cudaMemsetAsync(tgt.p + m, 0, 8 * 4, s));
     if (m) {
       DevBuf<uint64_t> keys, keys_alt;
       GB_TRY(keys.alloc(m));
@@ -721,7 +684,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       DevBuf<uint8_t> tmp;
       GB_TRY(tmp.alloc(tb));
       GB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, kb, m, 0, (int)(2 * bits), s));
-      k_unpack_low<<<grid_for(m, 256), 256, 0, s>>>(kb.Current(), m, bits, p->tgt.p);
+      k_unpack_low<<<grid_for(m, 256), 256, 0, s>>>(kb.Current(), m, bits, tgt.p);
       k_mark_ends_key<<<grid_for(m, 256), 256, 0, s>>>(kb.Current(), m, bits, p->off.p);
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
@@ -734,25 +697,74 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       GB_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, p->off.p, p->off.p, cub::Max(), (int64_t)n + 1, s));
       GB_CUDA(cudaStreamSynchronize(s));
     }
-    // 3. n_active = first row whose offset equals m (rows are ordered active-first)
+    // 3. row classes: rows are ordered by in-degree, so both classes are prefixes
     {
-      std::vector<uint32_t> probe(1);
-      // binary search on device memory through small copies (log2(n) 4-byte reads)
-      uint32_t lo = 0, hi = n;
-      while (lo < hi) {
-        uint32_t mid = lo + (hi - lo) / 2;
-        GB_CUDA(cudaMemcpyAsync(probe.data(), p->off.p + mid, 4, cudaMemcpyDeviceToHost, s));
-        GB_CUDA(cudaStreamSynchronize(s));
-        if (probe[0] < m) lo = mid + 1; else hi = mid;
-      }
-      // lo = first row r with off[r] >= m  => rows [lo, n) are empty, but row lo-1 may also be
-      // empty only if m == 0
-      p->n_active = (m == 0) ? 0 : lo;
+      DevBuf<uint32_t> counts;
+      GB_TRY(counts.alloc(2));
+      GB_CUDA(cudaMemsetAsync(counts.p, 0, 8, s));
+      k_count_rows<<<grid_for(n, 256), 256, 0, s>>>(p->off.p, n, counts.p);
+      uint32_t h[2] = {0, 0};
+      GB_CUDA(cudaMemcpyAsync(h, counts.p, 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      p->n_active = h[0];
+      p->n_long = h[1];
     }
-    p->hot_count = std::min<uint32_t>((uint32_t)PR_HOT, n & ~3u);
-    p->smem_bytes = (size_t)p->hot_count * sizeof(float) + (size_t)PR_WARPS * PR_WARP_SMEM;
-    GB_CUDA(cudaFuncSetAttribute(k_pr_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    // 3b. SELL-32 layout of rows [n_long, n_active)
+    p->num_slices = (p->n_active - p->n_long + 31) / 32;
+    if (p->num_slices) {
+      DevBuf<uint32_t> units, bases;
+      GB_TRY(units.alloc(p->num_slices));
+      GB_TRY(bases.alloc(p->num_slices));
+      k_sell_widths<<<grid_for(p->num_slices, 256), 256, 0, s>>>(p->off.p, p->n_long, p->num_slices, units.p);
+      size_t tb = 0;
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, units.p, bases.p, (int)p->num_slices, s));
+      DevBuf<uint8_t> tmp;
+      GB_TRY(tmp.alloc(tb));
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units.p, bases.p, (int)p->num_slices, s));
+      uint32_t last_base = 0, last_units = 0;
+      GB_CUDA(cudaMemcpyAsync(&last_base, bases.p + p->num_slices - 1, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(&last_units, units.p + p->num_slices - 1, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      const size_t total_units = (size_t)last_base + last_units;
+      GB_TRY(p->slice_meta.alloc(p->num_slices));
+      GB_TRY(p->sell.alloc(total_units, 64));
+      k_sell_meta<<<grid_for(p->num_slices, 256), 256, 0, s>>>(units.p, bases.p, p->num_slices, p->slice_meta.p);
+      k_sell_fill<<<grid_for((uint64_t)p->num_slices * 32, 256), 256, 0, s>>>(
+          p->off.p, tgt.p, p->n_long, p->n_active, p->num_slices, p->slice_meta.p, p->sell.p);
+      GB_CUDA(cudaGetLastError());
+      GB_CUDA(cudaStreamSynchronize(s));
+    }
+    // 3c. hub rows: padded 256-edge segments
+    p->num_segs = 0;
+    GB_TRY(p->seg_first.alloc((size_t)p->n_long + 1));
+    {
+      k_seg_counts<<<grid_for((uint64_t)p->n_long + 1, 256), 256, 0, s>>>(p->off.p, p->n_long, p->seg_first.p);
+      size_t tb = 0;
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p->seg_first.p, p->seg_first.p, (int)(p->n_long + 1), s));
+      DevBuf<uint8_t> tmp;
+      GB_TRY(tmp.alloc(tb));
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p->seg_first.p, p->seg_first.p, (int)(p->n_long + 1), s));
+      GB_CUDA(cudaMemcpyAsync(&p->num_segs, p->seg_first.p + p->n_long, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+    }
+    const size_t seg_slices = ((size_t)p->num_segs + 31) / 32;
+    GB_TRY(p->seg_tgt.alloc(seg_slices * 32 * (PR_SEG / 4), 64));
+    GB_CUDA(cudaMemsetAsync(p->seg_tgt.p, 0xFF, (seg_slices * 32 * (PR_SEG / 4) + 64) * sizeof(uint4), s));  // ~0 = padding
+    GB_TRY(p->partial.alloc(std::max<size_t>(p->num_segs, 1)));
+    if (p->num_segs) {
+      k_seg_fill<<<grid_for((uint64_t)p->n_long * 32, 256), 256, 0, s>>>(
+          p->off.p, tgt.p, p->seg_first.p, p->n_long, reinterpret_cast<uint32_t*>(p->seg_tgt.p));
+      GB_CUDA(cudaGetLastError());
+    }
+    GB_CUDA(cudaStreamSynchronize(s));
+    tgt.release();
+    uint32_t hot_cap = PR_HOT;
+    if (const char* e = getenv("GB_PR_HOT")) hot_cap = std::min<uint32_t>((uint32_t)PR_HOT_MAX, (uint32_t)atoi(e)) & ~3u;
+    p->hot_count = std::min<uint32_t>(hot_cap, n & ~3u);
+    p->smem_bytes = (size_t)p->hot_count * sizeof(float) + 16;
+    GB_CUDA(cudaFuncSetAttribute(k_pr_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     // 4. chunking of the whole active range + state vectors
     GB_TRY(build_range(g, p, 0, p->n_active, &p->all));
     GB_TRY(p->x[0].alloc(n));
@@ -771,21 +783,24 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
 
 static PrArgs make_args(const PrPlan* p, const PrRange* rg, float base, float damping, double tolerance) {
   PrArgs a{};
-  a.off = p->off.p;
-  a.tgt = p->tgt.p;
   a.outdeg = p->outdeg.p;
-  a.coord = rg->coord.p;
-  a.fix = rg->fix.p;
-  a.carry_tail = rg->carry_tail.p;
-  a.head_part = rg->head_part.p;
+  a.seg_tgt = p->seg_tgt.p;
+  a.seg_first = p->seg_first.p;
+  a.partial = p->partial.p;
+  a.seg_begin = rg->seg_begin;
+  a.seg_end = rg->seg_end;
+  a.long_begin = rg->long_begin;
+  a.long_end = rg->long_end;
+  a.sell = p->sell.p;
+  a.slice_meta = p->slice_meta.p;
+  a.slice_begin = rg->slice_begin;
+  a.slice_end = rg->slice_end;
+  a.sell_row0 = p->n_long;
+  a.sell_row_end = rg->sell_row_end;
   a.block_err = rg->block_err.p;
   a.err_hist = rg->err_hist.p;
   a.ctrl = rg->ctrl.p;
-  a.row_end = rg->row_end;
-  a.item_base = rg->item_base;
-  a.num_chunks = rg->num_chunks;
-  a.num_fix = rg->num_fix;
-  a.grid_pull = rg->grid_pull;
+  a.err_base_fin = rg->grid_sell;
   a.base = base;
   a.damping = damping;
   a.tolerance = tolerance;
@@ -866,10 +881,11 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
         ev_used += 2;
         GB_CUDA(cudaEventRecord(e0, s));
       }
-      if (rg->num_chunks) k_pr_pull<false><<<rg->grid_pull, PR_THREADS, p->smem_bytes, s>>>(a);
+      if (rg->grid_seg) k_pr_seg<<<rg->grid_seg, PR_THREADS, p->smem_bytes, s>>>(a);
+      if (rg->grid_sell) k_pr_sell<false><<<rg->grid_sell, PR_THREADS, p->smem_bytes, s>>>(a);
       if (e1) GB_CUDA(cudaEventRecord(e1, s));
-      k_pr_fix<false><<<rg->grid_fix, PR_FIX_THREADS, 0, s>>>(a);
-      g->timing.kernel_launches += rg->num_chunks ? 2 : 1;
+      k_pr_finish<false><<<rg->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+      g->timing.kernel_launches += 1 + (rg->grid_seg ? 1 : 0) + (rg->grid_sell ? 1 : 0);
       if (sweep_no == 1 && p->n_active < n) {
         // sources without in-edges change exactly once (init/deg -> base/deg): patch the buffer
         // sweep 1 has just finished reading
@@ -973,6 +989,16 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ra
     }
   }
   for (uint32_t i = count + 1; i <= parts; ++i) ranges[i] = p->n;
+  // boundaries inside the SELL region move to the nearest slice boundary (32 rows)
+  for (uint32_t i = 1; i < parts; ++i) {
+    uint32_t b = ranges[i];
+    if (b > p->n_long && b < p->n_active) {
+      b = p->n_long + ((b - p->n_long + 16) / 32) * 32;
+      if (b > p->n_active) b = p->n_active;
+    }
+    if (b < ranges[i - 1]) b = ranges[i - 1];
+    ranges[i] = b;
+  }
   return GB_OK;
 }
 
@@ -1061,12 +1087,13 @@ gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t swe
   a.extra_err = (sweep_no == 1 && rg->row_begin == 0)
                     ? (double)(p->n - p->n_active) * fabs((double)(base - init))
                     : 0.0;
+  if (rg->grid_seg) gb::k_pr_seg<<<rg->grid_seg, gb::PR_THREADS, p->smem_bytes, s>>>(a);
   if (peer_count) {
-    if (rg->num_chunks) gb::k_pr_pull<true><<<rg->grid_pull, gb::PR_THREADS, p->smem_bytes, s>>>(a);
-    gb::k_pr_fix<true><<<rg->grid_fix, gb::PR_FIX_THREADS, 0, s>>>(a);
+    if (rg->grid_sell) gb::k_pr_sell<true><<<rg->grid_sell, gb::PR_THREADS, p->smem_bytes, s>>>(a);
+    gb::k_pr_finish<true><<<rg->grid_fin, gb::PR_FIN_THREADS, 0, s>>>(a);
   } else {
-    if (rg->num_chunks) gb::k_pr_pull<false><<<rg->grid_pull, gb::PR_THREADS, p->smem_bytes, s>>>(a);
-    gb::k_pr_fix<false><<<rg->grid_fix, gb::PR_FIX_THREADS, 0, s>>>(a);
+    if (rg->grid_sell) gb::k_pr_sell<false><<<rg->grid_sell, gb::PR_THREADS, p->smem_bytes, s>>>(a);
+    gb::k_pr_finish<false><<<rg->grid_fin, gb::PR_FIN_THREADS, 0, s>>>(a);
   }
   if (sweep_no == 1 && p->n_active < p->n)
     gb::k_pr_fill_inactive<<<gb::grid_for(p->n - p->n_active, 256), 256, 0, s>>>(
@@ -1095,16 +1122,12 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32
   if (row_end) *row_end = rg->row_end;
   if (active_rows) *active_rows = shard->graph->pr_plan->n_active;
   if (edges) {
-    // items = edges + rows
-    uint64_t items = 0;
-    if (rg->num_chunks) {
-      uint2 c[2];
-      gb::DeviceGuard guard(shard->graph->device);
-      GB_CUDA(cudaMemcpy(&c[0], rg->coord.p, sizeof(uint2), cudaMemcpyDeviceToHost));
-      GB_CUDA(cudaMemcpy(&c[1], rg->coord.p + rg->num_chunks, sizeof(uint2), cudaMemcpyDeviceToHost));
-      items = (uint64_t)c[1].y - c[0].y;
-    }
-    *edges = items;
+    const gb::PrPlan* p = shard->graph->pr_plan;
+    uint32_t h[2] = {0, 0};
+    gb::DeviceGuard guard(shard->graph->device);
+    GB_CUDA(cudaMemcpy(&h[0], p->off.p + rg->row_begin, 4, cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemcpy(&h[1], p->off.p + rg->row_end, 4, cudaMemcpyDeviceToHost));
+    *edges = (uint64_t)h[1] - h[0];
   }
   return GB_OK;
 }
