@@ -8,9 +8,10 @@ A "step" is one pass of the hot path over one graph: `page_rank` with 20 forced 
 quoted on; it fits one B200).  One JSON line is printed by rank 0.
 
   value        m * sweeps * K / device time of K steps, graph resident in HBM, result left in HBM
-  e2e          same metric through the C ABI with HOST buffers: every step uploads the host CSR
-               (pinned), builds the device twin, runs page_rank and copies the ranks back
-  roofline     the dominant kernel (k_pr_pull) timed with CUDA events around every launch:
+  e2e          same metric through the C ABI with HOST buffers (gb_page_rank_csr_u32): every step uploads
+               the pinned host in-CSR + out offsets, builds the device layout, runs page_rank and
+               copies the ranks back; nothing stays resident between steps
+  roofline     the sweep kernels (k_pr_seg + k_pr_sell) timed with CUDA events around every sweep:
                algorithmic bytes (4m + 24n + 4 per sweep) / mean launch time vs measured HBM peak
   cpu_baseline the reference's multi-threaded in-place sweep (oracle.page_rank_mt, the C restatement
                of crates/algos/src/page_rank.rs:113-168) on the same graph, bounded sample
@@ -263,12 +264,9 @@ def run_single(args):
     cfg_h = _capi.PageRankConfig(SWEEPS, 0.0, DAMPING, _capi.PR_JACOBI)
 
     def e2e_step():
-        h = C.c_void_p()
-        check(lib.gb_digraph_from_csr_u32(0, n, out_off.ctypes.data_as(C.c_void_p), out_tgt.ctypes.data_as(C.c_void_p),
-                                          None, in_off.ctypes.data_as(C.c_void_p), in_tgt.ctypes.data_as(C.c_void_p),
-                                          C.byref(h)))
-        check(lib.gb_page_rank(h, C.byref(cfg_h), h_scores.ctypes.data_as(C.c_void_p), C.byref(it), C.byref(err)))
-        check(lib.gb_graph_free(h))
+        check(lib.gb_page_rank_csr_u32(0, n, in_off.ctypes.data_as(C.c_void_p), in_tgt.ctypes.data_as(C.c_void_p),
+                                       out_off.ctypes.data_as(C.c_void_p), C.byref(cfg_h),
+                                       h_scores.ctypes.data_as(C.c_void_p), C.byref(it), C.byref(err)))
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()  # warm-up
@@ -279,9 +277,10 @@ def run_single(args):
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     e2e = {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS",
-           "h2d_bytes_per_step": int(8 * m + 8 * (n + 1)), "d2h_bytes_per_step": int(4 * n),
+           "h2d_bytes_per_step": int(4 * m + 8 * (n + 1)), "d2h_bytes_per_step": int(4 * n),
            "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
-           "what": "gb_digraph_from_csr_u32(host CSR pair, pinned) + gb_page_rank(host scores) + gb_graph_free"}
+           "what": "gb_page_rank_csr_u32: pinned host in-CSR + out offsets -> device, layout build, 20 sweeps, "
+                   "ranks back to the host, everything freed (no resident state between steps)"}
 
     # CPU baseline on the same graph, bounded sample
     cpu = None

@@ -71,6 +71,8 @@ SIGNATURES = {
     "gb_make_degree_ordered": (C.c_int, [_P]),
     "gb_page_rank": (C.c_int, [_P, C.POINTER(PageRankConfig), _P, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "gb_page_rank_device": (C.c_int, [_P, C.POINTER(PageRankConfig), _P, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "gb_page_rank_csr_u32": (C.c_int, [C.c_int, C.c_uint32, _P, _P, _P, C.POINTER(PageRankConfig), _P,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "gb_wcc": (C.c_int, [_P, C.POINTER(WccConfig), _P]),
     "gb_wcc_device": (C.c_int, [_P, C.POINTER(WccConfig), _P]),
     "gb_sssp": (C.c_int, [_P, C.POINTER(SsspConfig), _P]),

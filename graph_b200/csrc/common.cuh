@@ -130,6 +130,9 @@ struct DeviceGuard {
 gb_status build_csr_device(cudaStream_t s, uint32_t n, uint32_t* d_rows, uint32_t* d_cols, float* d_w,
                            uint64_t count, gb_layout layout, DevCsr* csr);
 gb_status new_graph(int device, gb_graph_kind kind, uint32_t n, gb_graph** out);
+// uploads a host CSR (offsets always, targets/weights when non-null) and validates it on the device
+gb_status upload_host_csr(cudaStream_t s, uint32_t n, const uint32_t* off, const uint32_t* tgt, const float* w,
+                          DevCsr* csr, const char* what);
 
 inline unsigned grid_for(uint64_t items, unsigned block, unsigned max_blocks = 148u * 16u) {
   uint64_t b = (items + block - 1) / block;

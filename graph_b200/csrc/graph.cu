@@ -120,18 +120,17 @@ __global__ void k_dedup_flags(const uint64_t* __restrict__ keys, uint64_t count,
   }
 }
 
-// expands CSR offsets into one row id per entry (binary search per entry: O(len log n), no atomics)
+// expands CSR offsets into one row id per entry: one warp per row (coalesced stores, no searches)
 __global__ void k_expand_rows(const uint32_t* __restrict__ off, uint32_t n, uint64_t count,
                               uint32_t* __restrict__ rows) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t lo = 0, hi = n;  // find the last v with off[v] <= i
-    while (hi - lo > 1) {
-      uint32_t mid = lo + (hi - lo) / 2;
-      if (off[mid] <= i) lo = mid; else hi = mid;
-    }
-    rows[i] = lo;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t v = warp; v < n; v += nwarps) {
+    const uint32_t b = off[v], e = off[v + 1];
+    for (uint32_t i = b + lane; i < e; i += 32) rows[i] = v;
   }
+  (void)count;
 }
 
 __global__ void k_degrees(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ deg) {
@@ -345,22 +344,42 @@ static gb_status upload_csr(cudaStream_t s, uint32_t n, const uint32_t* off, con
 static gb_status validate_host_csr(uint32_t n, const uint32_t* off, const uint32_t* tgt, const char* what) {
   GB_REQUIRE(off != nullptr, "%s offsets is NULL", what);
   GB_REQUIRE(off[0] == 0, "%s offsets[0] must be 0", what);
-  for (uint32_t v = 0; v < n; ++v)
-    GB_REQUIRE(off[v] <= off[v + 1], "%s offsets not monotone at %u", what, v);
   GB_REQUIRE(off[n] == 0 || tgt != nullptr, "%s targets is NULL", what);
   return GB_OK;
 }
 
+__global__ void k_check_monotone(const uint32_t* __restrict__ off, uint32_t n, unsigned int* __restrict__ bad) {
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    if (off[v] > off[v + 1]) atomicAdd(bad, 1u);
+}
+
 static gb_status validate_device_targets(cudaStream_t s, uint32_t n, const DevCsr& c, const char* what) {
-  if (c.len == 0) return GB_OK;
   DevBuf<unsigned int> bad;
-  GB_TRY(bad.alloc(1));
-  GB_CUDA(cudaMemsetAsync(bad.p, 0, 4, s));
-  k_check_ids<<<grid_for(c.len, 256), 256, 0, s>>>(c.tgt.p, c.len, n, bad.p);
-  unsigned int nbad = 0;
-  GB_CUDA(cudaMemcpyAsync(&nbad, bad.p, 4, cudaMemcpyDeviceToHost, s));
+  GB_TRY(bad.alloc(2));
+  GB_CUDA(cudaMemsetAsync(bad.p, 0, 8, s));
+  if (c.len) k_check_ids<<<grid_for(c.len, 256), 256, 0, s>>>(c.tgt.p, c.len, n, bad.p);
+  k_check_monotone<<<grid_for(n, 256), 256, 0, s>>>(c.off.p, n, bad.p + 1);
+  unsigned int nbad[2] = {0, 0};
+  GB_CUDA(cudaMemcpyAsync(nbad, bad.p, 8, cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaStreamSynchronize(s));
-  GB_REQUIRE(nbad == 0, "%s CSR holds %u targets >= node_count %u", what, nbad, n);
+  GB_REQUIRE(nbad[1] == 0, "%s offsets are not monotone (%u rows)", what, nbad[1]);
+  GB_REQUIRE(nbad[0] == 0, "%s CSR holds %u targets >= node_count %u", what, nbad[0], n);
+  return GB_OK;
+}
+
+gb_status upload_host_csr(cudaStream_t s, uint32_t n, const uint32_t* off, const uint32_t* tgt, const float* w,
+                          DevCsr* csr, const char* what) {
+  GB_TRY(validate_host_csr(n, off, tgt ? tgt : off, what));
+  if (tgt) {
+    GB_TRY(upload_csr(s, n, off, tgt, w, csr));
+    return validate_device_targets(s, n, *csr, what);
+  }
+  // offsets only (degrees): no target array on the device
+  csr->len = off[n];
+  GB_TRY(csr->off.alloc((size_t)n + 1));
+  GB_CUDA(cudaMemcpyAsync(csr->off.p, off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s));
+  DevCsr none;
+  (void)none;
   return GB_OK;
 }
 
@@ -656,7 +675,7 @@ gb_status gb_to_undirected(const gb_graph* dg, gb_layout layout, gb_graph** grap
     std::lock_guard<std::mutex> lock(dg->mu);
     DevBuf<uint32_t> rows;
     GB_TRY(rows.alloc(m));
-    if (m) k_expand_rows<<<grid_for(m, 256), 256, 0, g->stream>>>(dg->out.off.p, dg->n, m, rows.p);
+    if (m) k_expand_rows<<<grid_for((uint64_t)dg->n * 32, 256), 256, 0, g->stream>>>(dg->out.off.p, dg->n, m, rows.p);
     GB_CUDA(cudaGetLastError());
     return graph_from_device_edges(g, rows.p, dg->out.tgt.p, nullptr, m, layout);
   }();
@@ -701,7 +720,7 @@ gb_status gb_make_degree_ordered(gb_graph* g) {
   GB_CUDA(cudaMemsetAsync(fresh.tgt.p + len, 0, 8 * 4, s));
   if (len) {
     GB_TRY(rows.alloc(len));
-    k_expand_rows<<<grid_for(len, 256), 256, 0, s>>>(g->out.off.p, n, len, rows.p);
+    k_expand_rows<<<grid_for((uint64_t)n * 32, 256), 256, 0, s>>>(g->out.off.p, n, len, rows.p);
     DevBuf<uint64_t> keys, keys_alt;
     GB_TRY(keys.alloc(len));
     GB_TRY(keys_alt.alloc(len));

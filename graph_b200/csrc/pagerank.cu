@@ -125,39 +125,17 @@ __global__ void k_perm_keys(const uint32_t* __restrict__ in_off, const uint32_t*
   }
 }
 __global__ void k_perm_scatter(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ out_off,
-                               uint32_t n, uint32_t* __restrict__ new_id, uint32_t* __restrict__ outdeg) {
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+                               const uint32_t* __restrict__ in_off, uint32_t n, uint32_t* __restrict__ new_id,
+                               uint32_t* __restrict__ outdeg, uint32_t* __restrict__ indeg) {
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x) {
+    if (r == n) {
+      indeg[n] = 0;
+      continue;
+    }
     uint32_t v = sorted_ids[r];
     new_id[v] = r;
     outdeg[r] = out_off[v + 1] - out_off[v];
-  }
-}
-// one warp per original row: keys of the renumbered in-CSR
-__global__ void k_perm_edge_keys(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                                 const uint32_t* __restrict__ new_id, uint32_t n, uint32_t bits,
-                                 uint64_t* __restrict__ keys) {
-  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t v = warp; v < n; v += nwarps) {
-    uint32_t b = in_off[v], e = in_off[v + 1];
-    if (b == e) continue;
-    uint64_t hi = (uint64_t)new_id[v] << bits;
-    for (uint32_t i = b + lane; i < e; i += 32) keys[i] = hi | new_id[in_tgt[i]];
-  }
-}
-__global__ void k_unpack_low(const uint64_t* __restrict__ keys, uint64_t count, uint32_t bits,
-                             uint32_t* __restrict__ tgt) {
-  uint64_t mask = (1ull << bits) - 1ull;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    tgt[i] = (uint32_t)(keys[i] & mask);
-}
-__global__ void k_mark_ends_key(const uint64_t* __restrict__ keys, uint64_t count, uint32_t bits,
-                                uint32_t* __restrict__ marks) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t r = (uint32_t)(keys[i] >> bits);
-    if (i + 1 == count || (uint32_t)(keys[i + 1] >> bits) != r) marks[r + 1] = (uint32_t)(i + 1);
+    indeg[r] = in_off[v + 1] - in_off[v];
   }
 }
 // ---- sweep kernels (JACOBI) ------------------------------------------------------------------
@@ -455,20 +433,22 @@ __global__ void k_seg_counts(const uint32_t* __restrict__ off, uint32_t n_long, 
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_long; r += gridDim.x * blockDim.x)
     cnt[r] = (r < n_long) ? (off[r + 1] - off[r] + PR_SEG - 1) / PR_SEG : 0;
 }
-// one warp per hub row: copy its targets into its padded segments (slice-interleaved layout:
-// segment s lives in slice s/32 as lane s%32; element j of it is component j%4 of group j/4)
-__global__ void k_seg_fill(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt,
+// one warp per hub row: copy its (renumbered) sources into its padded segments (slice-interleaved
+// layout: segment s lives in slice s/32 as lane s%32; element j of it is component j%4 of group j/4)
+__global__ void k_seg_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                           const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
                            const uint32_t* __restrict__ seg_first, uint32_t n_long, uint32_t* __restrict__ out) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r = warp; r < n_long; r += nwarps) {
-    const uint32_t b = off[r], d = off[r + 1] - b;
+    const uint32_t old = old_of[r];
+    const uint32_t b = in_off[old], d = in_off[old + 1] - b;
     const uint32_t s0 = seg_first[r];
     for (uint32_t j = lane; j < d; j += 32) {
       const uint32_t sg = s0 + j / PR_SEG, e = j % PR_SEG;
       const uint64_t idx = (((uint64_t)(sg / 32) * (PR_SEG / 4) + e / 4) * 32 + (sg % 32)) * 4 + (e % 4);
-      out[idx] = tgt[b + j];
+      out[idx] = new_id[in_tgt[b + j]];
     }
   }
 }
@@ -484,8 +464,9 @@ __global__ void k_sell_meta(const uint32_t* __restrict__ units, const uint32_t* 
   for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x)
     meta[sidx] = make_uint2(bases[sidx], units[sidx] / 32);
 }
-__global__ void k_sell_fill(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t row0,
-                            uint32_t row_end, uint32_t num_slices, const uint2* __restrict__ meta,
+__global__ void k_sell_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                            const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
+                            uint32_t row0, uint32_t row_end, uint32_t num_slices, const uint2* __restrict__ meta,
                             uint4* __restrict__ sell) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -495,16 +476,17 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ off, const uint32_t* __
     const uint32_t row = row0 + 32 * sidx + lane;
     uint32_t b = 0, d = 0;
     if (row < row_end) {
-      b = off[row];
-      d = off[row + 1] - b;
+      const uint32_t old = old_of[row];
+      b = in_off[old];
+      d = in_off[old + 1] - b;
     }
     for (uint32_t q = 0; q < m.y; ++q) {
       uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
       const uint32_t j = 4 * q;
-      if (j + 0 < d) v.x = tgt[b + j + 0];
-      if (j + 1 < d) v.y = tgt[b + j + 1];
-      if (j + 2 < d) v.z = tgt[b + j + 2];
-      if (j + 3 < d) v.w = tgt[b + j + 3];
+      if (j + 0 < d) v.x = new_id[in_tgt[b + j + 0]];
+      if (j + 1 < d) v.y = new_id[in_tgt[b + j + 1]];
+      if (j + 2 < d) v.z = new_id[in_tgt[b + j + 2]];
+      if (j + 3 < d) v.w = new_id[in_tgt[b + j + 3]];
       sell[m.x + q * 32 + lane] = v;
     }
   }
@@ -641,9 +623,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
   p->n = n;
   p->m = m;
   gb_status st = [&]() -> gb_status {
-    uint32_t bits = 1;
-    while (bits < 32 && (1ull << bits) < n) ++bits;
-    // 1. permutation: rows with in-edges first, then out-degree descending, then id
+    // 1. permutation: in-degree descending, then out-degree descending, then id
+    DevBuf<uint32_t> old_of;  // internal id -> original id (plan-time only)
     {
       DevBuf<uint64_t> keys, keys_alt;
       DevBuf<uint32_t> ids, ids_alt;
@@ -661,40 +642,24 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int)n, 0, 64, s));
       GB_TRY(p->new_id.alloc(n));
       GB_TRY(p->outdeg.alloc(n));
-      k_perm_scatter<<<grid_for(n, 256), 256, 0, s>>>(vb.Current(), g->out.off.p, n, p->new_id.p,
-                                                     p->outdeg.p);
+      GB_TRY(p->off.alloc((size_t)n + 1));
+      k_perm_scatter<<<grid_for(n, 256), 256, 0, s>>>(vb.Current(), g->out.off.p, g->in.off.p, n, p->new_id.p,
+                                                     p->outdeg.p, p->off.p);
+      GB_TRY(old_of.alloc(n));
+      GB_CUDA(cudaMemcpyAsync(old_of.p, vb.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
-    // 2. renumbered in-CSR (rows sorted by internal source id: hot sources first)
-    DevBuf<uint32_t> tgt;  // renumbered in-CSR targets: plan-time only, re-laid out below
-    GB_TRY(p->off.alloc((size_t)n + 1));
-    GB_TRY(tgt.alloc(m, 8));
-    GB_CUDA(cudaMemsetAsync(p->off.p, 0, ((size_t)n + 1) * 4, s));
-    GB_CUDA(cudaMemsetAsync(tgt.p + m, 0, 8 * 4, s));
-    if (m) {
-      DevBuf<uint64_t> keys, keys_alt;
-      GB_TRY(keys.alloc(m));
-      GB_TRY(keys_alt.alloc(m));
-      k_perm_edge_keys<<<grid_for((uint64_t)n * 32, 256), 256, 0, s>>>(g->in.off.p, g->in.tgt.p,
-                                                                      p->new_id.p, n, bits, keys.p);
-      cub::DoubleBuffer<uint64_t> kb(keys.p, keys_alt.p);
-      size_t tb = 0;
-      GB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, kb, m, 0, (int)(2 * bits), s));
-      DevBuf<uint8_t> tmp;
-      GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, kb, m, 0, (int)(2 * bits), s));
-      k_unpack_low<<<grid_for(m, 256), 256, 0, s>>>(kb.Current(), m, bits, tgt.p);
-      k_mark_ends_key<<<grid_for(m, 256), 256, 0, s>>>(kb.Current(), m, bits, p->off.p);
-      GB_CUDA(cudaGetLastError());
-      GB_CUDA(cudaStreamSynchronize(s));
-    }
+    // 2. internal offsets = running sum of the permuted in-degrees.  The rows themselves are never
+    //    materialised in internal order: the two layouts below are filled straight from the original
+    //    in-CSR through old_of / new_id (a row keeps its original entry order, which fixes the
+    //    summation order; no billion-key sort on the build path).
     {
       size_t tb = 0;
-      GB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb, p->off.p, p->off.p, cub::Max(), (int64_t)n + 1, s));
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p->off.p, p->off.p, (int64_t)n + 1, s));
       DevBuf<uint8_t> tmp;
       GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, p->off.p, p->off.p, cub::Max(), (int64_t)n + 1, s));
+      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p->off.p, p->off.p, (int64_t)n + 1, s));
       GB_CUDA(cudaStreamSynchronize(s));
     }
     // 3. row classes: rows are ordered by in-degree, so both classes are prefixes
@@ -730,7 +695,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       GB_TRY(p->sell.alloc(total_units, 64));
       k_sell_meta<<<grid_for(p->num_slices, 256), 256, 0, s>>>(units.p, bases.p, p->num_slices, p->slice_meta.p);
       k_sell_fill<<<grid_for((uint64_t)p->num_slices * 32, 256), 256, 0, s>>>(
-          p->off.p, tgt.p, p->n_long, p->n_active, p->num_slices, p->slice_meta.p, p->sell.p);
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, p->n_long, p->n_active, p->num_slices,
+          p->slice_meta.p, p->sell.p);
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
@@ -753,11 +719,11 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
     GB_TRY(p->partial.alloc(std::max<size_t>(p->num_segs, 1)));
     if (p->num_segs) {
       k_seg_fill<<<grid_for((uint64_t)p->n_long * 32, 256), 256, 0, s>>>(
-          p->off.p, tgt.p, p->seg_first.p, p->n_long, reinterpret_cast<uint32_t*>(p->seg_tgt.p));
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, p->seg_first.p, p->n_long,
+          reinterpret_cast<uint32_t*>(p->seg_tgt.p));
       GB_CUDA(cudaGetLastError());
     }
     GB_CUDA(cudaStreamSynchronize(s));
-    tgt.release();
     uint32_t hot_cap = PR_HOT;
     if (const char* e = getenv("GB_PR_HOT")) hot_cap = std::min<uint32_t>((uint32_t)PR_HOT_MAX, (uint32_t)atoi(e)) & ~3u;
     p->hot_count = std::min<uint32_t>(hot_cap, n & ~3u);
@@ -1143,6 +1109,22 @@ gb_status gb_page_rank(const gb_graph* graph, const gb_page_rank_config* config,
                        uint64_t* ran_iterations, double* error) {
   GB_REQUIRE(scores != nullptr, "scores is NULL");
   return gb::page_rank_impl(graph, config, nullptr, scores, ran_iterations, error);
+}
+
+gb_status gb_page_rank_csr_u32(int device, uint32_t n, const uint32_t* in_off, const uint32_t* in_tgt,
+                               const uint32_t* out_off, const gb_page_rank_config* config, float* scores,
+                               uint64_t* ran_iterations, double* error) {
+  GB_REQUIRE(scores != nullptr, "scores is NULL");
+  GB_REQUIRE(n > 0, "node_count must be > 0");
+  GB_REQUIRE(in_off && out_off, "offset arrays are NULL");
+  GB_REQUIRE(in_off[n] == out_off[n], "in and out offsets disagree on the edge count");
+  gb_graph* g = nullptr;
+  GB_TRY(gb::new_graph(device, GB_KIND_DIRECTED, n, &g));
+  gb_status st = gb::upload_host_csr(g->stream, n, in_off, in_tgt, nullptr, &g->in, "in");
+  if (st == GB_OK) st = gb::upload_host_csr(g->stream, n, out_off, nullptr, nullptr, &g->out, "out");
+  if (st == GB_OK) st = gb::page_rank_impl(g, config, nullptr, scores, ran_iterations, error);
+  gb_graph_free(g);
+  return st;
 }
 
 gb_status gb_page_rank_device(const gb_graph* graph, const gb_page_rank_config* config, float* d_scores,

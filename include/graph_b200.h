@@ -184,6 +184,15 @@ gb_status gb_page_rank(const gb_graph* graph, const gb_page_rank_config* config,
 gb_status gb_page_rank_device(const gb_graph* graph, const gb_page_rank_config* config,
                               float* d_scores, uint64_t* ran_iterations, double* error);
 
+/* One-shot form for a caller that holds the CSR on the host and wants no resident twin: exactly
+ * what page_rank reads through its trait bounds (page_rank.rs:61: Graph + DirectedDegrees +
+ * DirectedNeighbors) — the in-CSR and the out-degrees (given as out offsets).  Uploads
+ * 4m + 8(n+1) bytes instead of the full twin's 8m + 8(n+1). */
+gb_status gb_page_rank_csr_u32(int device, uint32_t node_count, const uint32_t* in_offsets,
+                               const uint32_t* in_targets, const uint32_t* out_offsets,
+                               const gb_page_rank_config* config, float* scores,
+                               uint64_t* ran_iterations, double* error);
+
 /* wcc_afforest(&graph, config).to_vec()                    wcc.rs:127-139, afforest.rs:100-114
  * components[v] = root of v = minimum node id of v's weakly connected component. */
 gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* components);

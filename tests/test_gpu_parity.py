@@ -399,3 +399,33 @@ def test_wrong_graph_kind_is_rejected(gb):
     out = C.c_void_p()
     assert lib.gb_to_undirected(u._g, 0, C.byref(out)) == 4
     assert lib.gb_page_rank(u._g, None, None, None, None) == 1  # GB_ERR_INVALID (NULL arguments)
+
+
+# ---- one-shot host-CSR entry point and input validation ----------------------------------------
+def test_page_rank_csr_one_shot_matches_resident_twin(gb, rmat16):
+    import ctypes as C
+    from graph_b200 import _capi
+    from graph_b200._capi import lib, check
+    src, dst, n, out, inc = rmat16
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for mode, maxit in ((_capi.PR_JACOBI, 20), (_capi.PR_EXACT, 5)):
+        cfg = _capi.PageRankConfig(maxit, 0.0, 0.85, mode)
+        scores = np.empty(n, np.float32)
+        it, err = C.c_uint64(0), C.c_double(0.0)
+        check(lib.gb_page_rank_csr_u32(0, n, P(inc[0]), P(inc[1]), P(out[0]), C.byref(cfg), P(scores), C.byref(it),
+                                       C.byref(err)))
+        g = gb.DiGraph.from_csr(out[0], out[1], inc[0], inc[1])
+        want = g.page_rank(max_iterations=maxit, tolerance=0.0, mode="jacobi" if mode == _capi.PR_JACOBI else "exact")
+        assert it.value == maxit and scores.tobytes() == want.scores().tobytes() and err.value == want.error
+
+
+def test_invalid_host_csr_is_rejected(gb):
+    off = np.array([0, 2, 3], np.uint32)
+    tgt = np.array([1, 7, 0], np.uint32)          # 7 >= n
+    with pytest.raises(ValueError, match="targets >= node_count"):
+        gb.DiGraph.from_csr(off, tgt, off, np.array([1, 0, 0], np.uint32))
+    bad_off = np.array([0, 3, 2], np.uint32)      # not monotone
+    with pytest.raises(ValueError):
+        gb.Graph.from_csr(bad_off, np.array([1, 0], np.uint32))
+    with pytest.raises(ValueError, match="out of range|>= node_count"):
+        gb.DiGraph.from_numpy(np.array([[0, 9]], dtype=np.uint32), node_count=4)
