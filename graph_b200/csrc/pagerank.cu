@@ -943,12 +943,19 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ra
   std::vector<uint32_t> off((size_t)p->n + 1);
   GB_CUDA(cudaMemcpyAsync(off.data(), p->off.p, off.size() * 4, cudaMemcpyDeviceToHost, g->stream));
   GB_CUDA(cudaStreamSynchronize(g->stream));
-  const uint64_t batch = (p->m + parts - 1) / parts;
+  // node_map = in-degree + a constant per-row charge: a row costs its gathers plus ~5 vector accesses,
+  // a division and (multi-GPU) one store per peer, so ranks owning millions of 1-edge rows would
+  // otherwise be the stragglers.  GB_SHARD_ROW_COST overrides the charge (0 = the plain rule).
+  uint64_t row_cost = 8;
+  if (const char* e = getenv("GB_SHARD_ROW_COST")) row_cost = (uint64_t)atoll(e);
+  const uint64_t total = p->m + row_cost * p->n_active;
+  const uint64_t batch = (total + parts - 1) / parts;
   uint32_t count = 0;
   uint64_t acc = 0;
   ranges[0] = 0;
   for (uint32_t v = 0; v < p->n; ++v) {
-    acc += off[v + 1] - off[v];
+    const uint32_t d = off[v + 1] - off[v];
+    acc += d + (d ? row_cost : 0);
     if ((count < parts - 1 && acc >= batch) || v == p->n - 1) {
       ranges[++count] = v + 1;
       acc = 0;

@@ -94,8 +94,9 @@ class ShardedPageRank:
         b = self.backend
         self.n, self.n_active, self.ranges = b.n, b.n_active, b.ranges
         dev = b.device
-        self.exchange = "nccl"
+        self.exchange = exchange if exchange in ("nccl", "allgather") else "nccl"
         self._peer_next = [None, None]
+        self.diag = None
         self.x = None
         if exchange in ("auto", "peer") and dev.type == "cuda" and self.world > 1:
             try:
@@ -131,6 +132,12 @@ class ShardedPageRank:
     def _exchange(self, x_next):
         if self.exchange == "peer":
             return  # the kernel already stored the slice into every peer
+        if self.exchange == "allgather":
+            # one grouped collective: every rank's (uneven) slice lands in place in every x_next
+            views = [x_next[min(self.ranges[p], self.n_active):min(self.ranges[p + 1], self.n_active)]
+                     for p in range(self.world)]
+            dist.all_gather(views, views[self.rank], group=self.group)
+            return
         for p in range(self.world):
             lo, hi = min(self.ranges[p], self.n_active), min(self.ranges[p + 1], self.n_active)
             if hi > lo:
@@ -144,12 +151,21 @@ class ShardedPageRank:
             dist.barrier(group=self.group)  # nobody may store into a peer that is still initialising
         sweep = 0
         limit = max_iterations if max_iterations else 100000
+        diag = self.diag
         while True:
             sweep += 1
             cur, nxt = self.x[(sweep - 1) & 1], self.x[sweep & 1]
             peers = self._peer_next[sweep & 1] if self.exchange == "peer" else None
+            if diag is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             b.step(damping, sweep, cur, nxt, peers, self.scores, self.err)
+            if diag is not None:
+                ev[1].record()
             self._exchange(nxt)
+            if diag is not None:
+                ev[2].record()
+                diag.append(ev)
             # total error of the sweep; also the barrier that orders the peer stores of sweep k before
             # any rank's reads in sweep k+1
             dist.all_reduce(self.err, op=dist.ReduceOp.SUM, group=self.group)
@@ -163,6 +179,13 @@ class ShardedPageRank:
         if not tolerance > 0.0:
             self.error = float(self.err.item())
         return self
+
+    def diag_summary(self):
+        """(mean kernel ms, mean exchange ms) per sweep of the recorded run (diagnostics only)."""
+        torch.cuda.synchronize()
+        k = [a.elapsed_time(b) for a, b, _ in self.diag]
+        x = [b.elapsed_time(c) for _, b, c in self.diag]
+        return float(np.mean(k)), float(np.mean(x))
 
     def scores_device(self):
         """Full score vector in original ids on this rank's device (exchanges the score slices)."""
