@@ -935,7 +935,7 @@ struct gb_pr_shard {
 
 namespace gb {
 
-static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ranges) {
+static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row_cost, uint32_t* ranges) {
   // greedy_node_map_partition (graph_ops.rs:479-509) over the INTERNAL row order with
   // node_map = in-degree and batch = ceil(m / parts) (in_degree_partition, graph_ops.rs:431-439)
   if (!g->pr_plan) GB_TRY(build_pr_plan(g, &g->pr_plan));
@@ -946,7 +946,6 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ra
   // node_map = in-degree + a constant per-row charge: a row costs its gathers plus ~5 vector accesses,
   // a division and (multi-GPU) one store per peer, so ranks owning millions of 1-edge rows would
   // otherwise be the stragglers.  GB_SHARD_ROW_COST overrides the charge (0 = the plain rule).
-  uint64_t row_cost = 8;
   if (const char* e = getenv("GB_SHARD_ROW_COST")) row_cost = (uint64_t)atoll(e);
   const uint64_t total = p->m + row_cost * p->n_active;
   const uint64_t batch = (total + parts - 1) / parts;
@@ -979,13 +978,13 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ra
 
 extern "C" {
 
-gb_status gb_pr_shard_partition(const gb_graph* g, uint32_t parts, uint32_t* ranges) {
+gb_status gb_pr_shard_partition(const gb_graph* g, uint32_t parts, uint32_t row_cost, uint32_t* ranges) {
   GB_REQUIRE(g && ranges, "NULL argument");
   GB_REQUIRE(parts >= 1, "parts must be >= 1");
   if (g->kind != GB_KIND_DIRECTED) return gb::fail(GB_ERR_UNSUPPORTED, "page rank shards need a directed graph");
   gb::DeviceGuard guard(g->device);
   std::lock_guard<std::mutex> lock(g->mu);
-  return gb::shard_partition(g, parts, ranges);
+  return gb::shard_partition(g, parts, row_cost, ranges);
 }
 
 gb_status gb_pr_shard_create(const gb_graph* g, uint32_t row_begin, uint32_t row_end, gb_pr_shard** shard) {

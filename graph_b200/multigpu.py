@@ -31,12 +31,12 @@ from ._capi import check, lib
 class CudaShardBackend:
     """The product backend: gb_pr_shard_* of libgraph_b200.so on this rank's GPU."""
 
-    def __init__(self, graph, rank: int, world: int):
+    def __init__(self, graph, rank: int, world: int, row_cost: int = 3):
         self.graph = graph
         self.n = graph.node_count()
         self.device = torch.device("cuda", torch.cuda.current_device())
         ranges = np.zeros(world + 1, np.uint32)
-        check(lib.gb_pr_shard_partition(graph._g, world, ranges.ctypes.data_as(C.c_void_p)))
+        check(lib.gb_pr_shard_partition(graph._g, world, row_cost, ranges.ctypes.data_as(C.c_void_p)))
         self.ranges = [int(v) for v in ranges]
         self._shard = C.c_void_p()
         check(lib.gb_pr_shard_create(graph._g, self.ranges[rank], self.ranges[rank + 1], C.byref(self._shard)))
@@ -90,7 +90,11 @@ class ShardedPageRank:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.backend = backend if backend is not None else CudaShardBackend(graph, self.rank, self.world)
+        # per-row charge of the partition: ~2 edge-equivalents of vector traffic, plus (fused exchange)
+        # one remote store per peer — measured 18 with 7 peers (profiles/r01_multigpu_diag.txt)
+        want_peer = exchange in ("auto", "peer") and torch.cuda.is_available() and self.world > 1
+        row_cost = 4 + 2 * (self.world - 1) if want_peer else 3
+        self.backend = backend if backend is not None else CudaShardBackend(graph, self.rank, self.world, row_cost)
         b = self.backend
         self.n, self.n_active, self.ranges = b.n, b.n_active, b.ranges
         dev = b.device

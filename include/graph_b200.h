@@ -218,8 +218,12 @@ typedef struct gb_pr_shard gb_pr_shard;
 /* the reference's own partitioner on the ORIGINAL ids: in_degree_partition (graph_ops.rs:431-439,
  * :479-509); ranges has parts+1 entries */
 gb_status gb_in_degree_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
-/* same greedy rule applied to the internal row order: ranges[0..parts] (parts+1 entries) */
-gb_status gb_pr_shard_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
+/* same greedy rule applied to the internal row order with node_map = in-degree + row_cost for rows
+ * that have in-edges: ranges[0..parts] (parts+1 entries).  row_cost = 0 is the reference's plain
+ * in_degree_partition; a row also costs ~5 vector accesses and, on the fused path, one remote store
+ * per peer — measured ~2 edge-equivalents without and ~18 with 7 peers (profiles/r01_multigpu_diag.txt) */
+gb_status gb_pr_shard_partition(const gb_graph* graph, uint32_t parts, uint32_t row_cost,
+                                uint32_t* ranges);
 gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t row_begin, uint32_t row_end,
                              gb_pr_shard** shard);
 gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32_t* row_end,
