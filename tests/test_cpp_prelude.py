@@ -1,0 +1,35 @@
+"""The C++ host API (include/graph_b200.hpp, the graph::prelude mirror): compiles and links against the
+C ABI on CPU; on a GPU box the demo reproduces the reference's goldens through it."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def build_demo(tmp_path):
+    exe = tmp_path / "prelude_demo"
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
+           str(ROOT / "tests" / "cpp" / "prelude_demo.cpp"), "-o", str(exe), f"-L{ROOT / 'graph_b200'}",
+           "-lgraph_b200", f"-Wl,-rpath,{ROOT / 'graph_b200'}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_prelude_header_compiles_and_links(tmp_path):
+    import torch
+    exe = build_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("covered by the gpu test")
+    # without a GPU the library must fail loudly, not fall back: graph::Error GB_ERR_CUDA (2)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_prelude_demo_reproduces_reference_goldens(tmp_path):
+    exe = build_demo(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "prelude_demo ok" in r.stdout
