@@ -40,10 +40,11 @@ __global__ void k_cc_init(uint32_t* __restrict__ parent, uint32_t n) {
 
 // sample_subgraph, wcc.rs:186-204: link u with its first `rounds` out-neighbours
 __global__ void k_cc_sample(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t n,
-                            uint32_t round, uint32_t* parent) {
+                            uint32_t rounds, uint32_t* parent) {
   for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     const uint32_t b = off[u], e = off[u + 1];
-    if (b + round < e) af_link(parent, u, tgt[b + round]);
+    const uint32_t lim = (e - b < rounds) ? e : b + rounds;  // out_neighbors(u).take(neighbor_rounds)
+    for (uint32_t i = b; i < lim; ++i) af_link(parent, u, tgt[i]);
   }
 }
 
@@ -83,16 +84,34 @@ __global__ void k_cc_link_remaining(const uint32_t* __restrict__ out_off, const 
   for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
     const uint32_t mine = base + lane;
     bool live = mine < n;
+    uint32_t ob = 0, oe = 0, ib = 0, ie = 0;
+    if (live) {
+      // offsets are read lane-parallel (coalesced); vertices without remaining edges (all isolated
+      // vertices, ~half of an R-MAT graph) never enter the warp-serial part
+      ob = out_off[mine];
+      oe = out_off[mine + 1];
+      ib = in_off[mine];
+      ie = in_off[mine + 1];
+      ob = (oe - ob > rounds) ? ob + rounds : oe;
+      live = (oe > ob) || (ie > ib);
+    }
     if (live && use_skip) live = ld_parent(parent, mine) != skip;
-    unsigned mask = __ballot_sync(0xFFFFFFFFu, live);
+    // short lists are linked by their own lane; long ones are served by the whole warp
+    const uint32_t work = (oe - ob) + (ie - ib);
+    const bool small = live && work <= 8;
+    if (small) {
+      for (uint32_t i = ob; i < oe; ++i) af_link(parent, mine, out_tgt[i]);
+      for (uint32_t i = ib; i < ie; ++i) af_link(parent, mine, in_tgt[i]);
+    }
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, live && !small);
     while (mask) {
-      const uint32_t u = base + (__ffs(mask) - 1);
+      const int owner = __ffs(mask) - 1;
       mask &= mask - 1;
-      const uint32_t ob = out_off[u], oe = out_off[u + 1];
-      if (oe - ob > rounds)
-        for (uint32_t i = ob + rounds + lane; i < oe; i += 32) af_link(parent, u, out_tgt[i]);
-      const uint32_t ib = in_off[u], ie = in_off[u + 1];
-      for (uint32_t i = ib + lane; i < ie; i += 32) af_link(parent, u, in_tgt[i]);
+      const uint32_t u = base + owner;
+      const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, ob, owner), e0 = __shfl_sync(0xFFFFFFFFu, oe, owner);
+      const uint32_t b1 = __shfl_sync(0xFFFFFFFFu, ib, owner), e1 = __shfl_sync(0xFFFFFFFFu, ie, owner);
+      for (uint32_t i = b0 + lane; i < e0; i += 32) af_link(parent, u, out_tgt[i]);
+      for (uint32_t i = b1 + lane; i < e1; i += 32) af_link(parent, u, in_tgt[i]);
     }
   }
 }
@@ -116,12 +135,11 @@ static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t*
   const unsigned grid = grid_for(n, blk);
   const uint32_t rounds = (uint32_t)std::min<uint64_t>(cfg->neighbor_rounds, 0xFFFFFFFFull);
   k_cc_init<<<grid, blk, 0, s>>>(d_comp, n);
-  // `take(neighbor_rounds)` (wcc.rs:198) never looks past the row, so rounds beyond the largest
-  // out-degree are no-ops; cap the launch count accordingly
-  const uint32_t sample_rounds = std::min<uint32_t>(rounds, 64);
-  for (uint32_t r = 0; r < sample_rounds; ++r) k_cc_sample<<<grid, blk, 0, s>>>(g->out.off.p, g->out.tgt.p, n, r, d_comp);
+  // sample_subgraph, wcc.rs:186-204: every vertex links its first `neighbor_rounds` out-neighbours
+  const uint32_t sample_rounds = rounds;
+  if (sample_rounds) k_cc_sample<<<grid, blk, 0, s>>>(g->out.off.p, g->out.tgt.p, n, sample_rounds, d_comp);
   k_cc_compress<<<grid, blk, 0, s>>>(d_comp, n);
-  g->timing.kernel_launches += 2 + sample_rounds;
+  g->timing.kernel_launches += 2 + (sample_rounds ? 1 : 0);
   // find_largest_component, wcc.rs:245-271 (which component is skipped never changes the result)
   uint32_t skip = 0;
   int use_skip = 0;
@@ -145,8 +163,6 @@ static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t*
     use_skip = 1;
     g->timing.kernel_launches += 1;
   }
-  // a sampled round count beyond 64 would leave out-edges [64, rounds) unprocessed in phase 1;
-  // link_remaining then starts from the rounds actually sampled so that every edge is seen
   k_cc_link_remaining<<<grid_for((uint64_t)n, blk), blk, 0, s>>>(g->out.off.p, g->out.tgt.p, g->in.off.p,
                                                                g->in.tgt.p, n, sample_rounds, skip, use_skip,
                                                                d_comp);
