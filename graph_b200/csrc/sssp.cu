@@ -29,33 +29,71 @@ __global__ void k_sssp_init(uint32_t* __restrict__ dist, uint32_t n, uint32_t st
     dist[v] = (v == start) ? 0u : __float_as_uint(FLT_MAX);  // INF = f32::MAX, sssp.rs:12
 }
 
-// relax_edges, sssp.rs:170-204, for every vertex of the near queue; one warp per vertex
+// relax_edges, sssp.rs:170-204, for every vertex of the near queue.  One lane per queue entry; short
+// adjacency lists are relaxed by their own lane, long ones by the whole warp.
+// queue slot reservation, aggregated over the lanes that are appending right now: one atomicAdd per
+// group of converged lanes instead of one per successful relaxation (a single hot counter otherwise
+// serialises every append of the pass)
+__device__ __forceinline__ uint32_t sssp_reserve(uint32_t* counter) {
+  const unsigned active = __activemask();
+  const int leader = __ffs(active) - 1;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(active));
+  base = __shfl_sync(active, base, leader);
+  return base + __popc(active & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void sssp_relax_edge(const uint32_t* __restrict__ tgt, const float* __restrict__ w,
+                                                uint32_t* dist, uint32_t i, float du, float upper,
+                                                uint32_t* __restrict__ near_out, uint32_t* __restrict__ far,
+                                                uint32_t* counts, uint32_t cap) {
+  const uint32_t t = tgt[i];
+  const float nd = __fadd_rn(du, w[i]);
+  const uint32_t nb = __float_as_uint(nd);
+  const uint32_t old = atomicMin(dist + t, nb);  // the CAS-min loop of sssp.rs:184-202
+  if (nb < old) {
+    if (nd < upper) {
+      const uint32_t pos = sssp_reserve(counts + 0);
+      if (pos < cap) near_out[pos] = t;
+    } else {
+      const uint32_t pos = sssp_reserve(counts + 1);
+      if (pos < cap) far[pos] = t;
+    }
+  }
+}
+
 __global__ void k_sssp_relax(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt,
                              const float* __restrict__ w, uint32_t* dist, const uint32_t* __restrict__ queue,
                              uint32_t count, float lower, float upper, uint32_t* __restrict__ near_out,
                              uint32_t* __restrict__ far, uint32_t* counts, uint32_t cap) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t q = warp; q < count; q += nwarps) {
-    const uint32_t u = queue[q];
-    const float du = __uint_as_float(*((volatile uint32_t*)(dist + u)));
-    if (du < lower) continue;  // stale entry: settled in an earlier bucket (sssp.rs:126)
-    const uint32_t b = off[u], e = off[u + 1];
-    for (uint32_t i = b + lane; i < e; i += 32) {
-      const uint32_t t = tgt[i];
-      const float nd = __fadd_rn(du, w[i]);
-      const uint32_t nb = __float_as_uint(nd);
-      const uint32_t old = atomicMin(dist + t, nb);
-      if (nb < old) {
-        if (nd < upper) {
-          uint32_t pos = atomicAdd(counts + 0, 1u);
-          if (pos < cap) near_out[pos] = t;
-        } else {
-          uint32_t pos = atomicAdd(counts + 1, 1u);
-          if (pos < cap) far[pos] = t;
-        }
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  for (uint32_t qb = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; qb < count; qb += nthreads) {
+    const uint32_t q = qb + lane;
+    uint32_t b = 0, e = 0;
+    float du = 0.0f;
+    bool live = q < count;
+    if (live) {
+      const uint32_t u = queue[q];
+      du = __uint_as_float(*((volatile uint32_t*)(dist + u)));
+      live = !(du < lower);  // stale entry: settled in an earlier bucket (sssp.rs:126)
+      if (live) {
+        b = off[u];
+        e = off[u + 1];
+        live = e > b;
       }
+    }
+    const bool small = live && (e - b) <= 8;
+    if (small)
+      for (uint32_t i = b; i < e; ++i) sssp_relax_edge(tgt, w, dist, i, du, upper, near_out, far, counts, cap);
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, live && !small);
+    while (mask) {
+      const int owner = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t ob = __shfl_sync(0xFFFFFFFFu, b, owner), oe = __shfl_sync(0xFFFFFFFFu, e, owner);
+      const float odu = __shfl_sync(0xFFFFFFFFu, du, owner);
+      for (uint32_t i = ob + lane; i < oe; i += 32) sssp_relax_edge(tgt, w, dist, i, odu, upper, near_out, far, counts, cap);
     }
   }
 }
@@ -70,10 +108,10 @@ __global__ void k_sssp_split_far(const uint32_t* __restrict__ dist, const uint32
     const float d = __uint_as_float(dist[t]);
     if (d < lower) continue;
     if (d < upper) {
-      uint32_t pos = atomicAdd(counts + 0, 1u);
+      uint32_t pos = sssp_reserve(counts + 0);
       if (pos < cap) near_out[pos] = t;
     } else {
-      uint32_t pos = atomicAdd(counts + 2, 1u);
+      uint32_t pos = sssp_reserve(counts + 2);
       if (pos < cap) far_out[pos] = t;
     }
   }
@@ -142,7 +180,7 @@ static gb_status sssp_impl(const gb_graph* g, const gb_sssp_config* cfg, float* 
     while (near_count > 0) {
       const uint32_t zero2[2] = {0u, far_count};
       GB_CUDA(cudaMemcpyAsync(counts.p, zero2, 8, cudaMemcpyHostToDevice, s));
-      k_sssp_relax<<<grid_for((uint64_t)near_count * 32, blk), blk, 0, s>>>(
+      k_sssp_relax<<<grid_for((uint64_t)near_count, blk), blk, 0, s>>>(
           g->out.off.p, g->out.tgt.p, g->out.w.p, dist, near_in, near_count, lower, upper, near_out, far,
           counts.p, cap);
       g->timing.kernel_launches += 1;

@@ -63,24 +63,50 @@ __global__ void __launch_bounds__(256) k_tc(const uint32_t* __restrict__ off, co
         live = ve > vb && ue > ub;
       }
     }
-    const bool is_short = live && (ve - vb) <= TC_SHORT;
+    // The sum over w-occurrences of N(v) found in set(N(u)) equals the sum over DISTINCT x of N(u) of
+    // x's multiplicity in N(v); walk whichever list makes the lookups cheaper.
+    bool by_u = false;
+    if (live) {
+      const uint32_t lv = ve - vb, lu = ue - ub;
+      by_u = (uint64_t)lu * (32 - __clz(lv)) < (uint64_t)lv * (32 - __clz(lu));
+    }
+    const uint32_t walk_b = by_u ? ub : vb, walk_e = by_u ? ue : ve;
+    const uint32_t find_b = by_u ? vb : ub, find_e = by_u ? ve : ue;
+    const bool is_short = live && (walk_e - walk_b) <= TC_SHORT;
     if (is_short) {
-      for (uint32_t j = vb; j < ve; ++j) {
+      uint32_t prev = 0xFFFFFFFFu;
+      for (uint32_t j = walk_b; j < walk_e; ++j) {
         const uint32_t w = __ldg(tgt + j);
-        const uint32_t p = tc_lower_bound(tgt, ub, ue, w);
-        count += (p < ue && __ldg(tgt + p) == w) ? 1u : 0u;
+        if (by_u) {
+          if (w != prev) {
+            const uint32_t lo = tc_lower_bound(tgt, find_b, find_e, w);
+            count += tc_upper_bound(tgt, lo, find_e, w) - lo;
+          }
+          prev = w;
+        } else {
+          const uint32_t p = tc_lower_bound(tgt, find_b, find_e, w);
+          count += (p < find_e && __ldg(tgt + p) == w) ? 1u : 0u;
+        }
       }
     }
     unsigned long_mask = __ballot_sync(0xFFFFFFFFu, live && !is_short);
     while (long_mask) {
       const int owner = __ffs(long_mask) - 1;
       long_mask &= long_mask - 1;
-      const uint32_t oub = __shfl_sync(0xFFFFFFFFu, ub, owner), oue = __shfl_sync(0xFFFFFFFFu, ue, owner);
-      const uint32_t ovb = __shfl_sync(0xFFFFFFFFu, vb, owner), ove = __shfl_sync(0xFFFFFFFFu, ve, owner);
-      for (uint32_t j = ovb + lane; j < ove; j += 32) {
+      const uint32_t owb = __shfl_sync(0xFFFFFFFFu, walk_b, owner), owe = __shfl_sync(0xFFFFFFFFu, walk_e, owner);
+      const uint32_t ofb = __shfl_sync(0xFFFFFFFFu, find_b, owner), ofe = __shfl_sync(0xFFFFFFFFu, find_e, owner);
+      const bool oby_u = __shfl_sync(0xFFFFFFFFu, (int)by_u, owner) != 0;
+      for (uint32_t j = owb + lane; j < owe; j += 32) {
         const uint32_t w = __ldg(tgt + j);
-        const uint32_t p = tc_lower_bound(tgt, oub, oue, w);
-        count += (p < oue && __ldg(tgt + p) == w) ? 1u : 0u;
+        if (oby_u) {
+          if (j == owb || __ldg(tgt + j - 1) != w) {  // first occurrence of x in N(u)
+            const uint32_t lo = tc_lower_bound(tgt, ofb, ofe, w);
+            count += tc_upper_bound(tgt, lo, ofe, w) - lo;
+          }
+        } else {
+          const uint32_t p = tc_lower_bound(tgt, ofb, ofe, w);
+          count += (p < ofe && __ldg(tgt + p) == w) ? 1u : 0u;
+        }
       }
     }
   }
