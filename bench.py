@@ -327,6 +327,9 @@ def run_multi(args):
     m = EDGE_FACTOR * n
     g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
     spr = ShardedPageRank(g, exchange=args.exchange)
+    calibration = None
+    if not args.no_calibrate:
+        calibration = spr.calibrate()  # setup (like the layout build): measured-time shard rebalancing
     for _ in range(max(args.warmup, 3)):
         spr.run(SWEEPS, DAMPING)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -397,6 +400,7 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl", "allgather"])
+    ap.add_argument("--no-calibrate", action="store_true", help="multi-GPU: keep the static shard partition")
     ap.add_argument("--diag", action="store_true", help="multi-GPU: print per-rank kernel / exchange ms per sweep")
     args = ap.parse_args()
     if args.impl == "reference":

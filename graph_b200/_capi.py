@@ -79,7 +79,7 @@ SIGNATURES = {
     "gb_sssp_device": (C.c_int, [_P, C.POINTER(SsspConfig), _P]),
     "gb_triangle_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gb_in_degree_partition": (C.c_int, [_P, C.c_uint32, _P]),
-    "gb_pr_shard_partition": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
+    "gb_pr_shard_partition": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
     "gb_pr_shard_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "gb_pr_shard_info": (C.c_int, [_P, _P, _P, _P, _P]),
     "gb_pr_shard_init": (C.c_int, [_P, C.c_float, _P, _P, _P, _P]),

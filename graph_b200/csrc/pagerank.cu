@@ -935,7 +935,8 @@ struct gb_pr_shard {
 
 namespace gb {
 
-static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row_cost, uint32_t* ranges) {
+static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row_cost, const double* cuts,
+                                 uint32_t* ranges) {
   // greedy_node_map_partition (graph_ops.rs:479-509) over the INTERNAL row order with
   // node_map = in-degree and batch = ceil(m / parts) (in_degree_partition, graph_ops.rs:431-439)
   if (!g->pr_plan) GB_TRY(build_pr_plan(g, &g->pr_plan));
@@ -952,12 +953,25 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row
   uint32_t count = 0;
   uint64_t acc = 0;
   ranges[0] = 0;
-  for (uint32_t v = 0; v < p->n; ++v) {
-    const uint32_t d = off[v + 1] - off[v];
-    acc += d + (d ? row_cost : 0);
-    if ((count < parts - 1 && acc >= batch) || v == p->n - 1) {
-      ranges[++count] = v + 1;
-      acc = 0;
+  if (cuts) {
+    // explicit cut points (fractions of the total weight, increasing): used by the measured-time
+    // rebalancing of the multi-GPU orchestration
+    for (uint32_t k = 0; k + 1 < parts; ++k)
+      GB_REQUIRE(cuts[k] > 0.0 && cuts[k] < 1.0 && (k == 0 || cuts[k] >= cuts[k - 1]), "bad cut fraction %u", k);
+    for (uint32_t v = 0; v < p->n && count < parts - 1; ++v) {
+      const uint32_t d = off[v + 1] - off[v];
+      acc += d + (d ? row_cost : 0);
+      while (count < parts - 1 && (double)acc >= cuts[count] * (double)total) ranges[++count] = v + 1;
+    }
+    while (count < parts) ranges[++count] = p->n;
+  } else {
+    for (uint32_t v = 0; v < p->n; ++v) {
+      const uint32_t d = off[v + 1] - off[v];
+      acc += d + (d ? row_cost : 0);
+      if ((count < parts - 1 && acc >= batch) || v == p->n - 1) {
+        ranges[++count] = v + 1;
+        acc = 0;
+      }
     }
   }
   for (uint32_t i = count + 1; i <= parts; ++i) ranges[i] = p->n;
@@ -978,13 +992,14 @@ static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row
 
 extern "C" {
 
-gb_status gb_pr_shard_partition(const gb_graph* g, uint32_t parts, uint32_t row_cost, uint32_t* ranges) {
+gb_status gb_pr_shard_partition(const gb_graph* g, uint32_t parts, uint32_t row_cost, const double* cuts,
+                                uint32_t* ranges) {
   GB_REQUIRE(g && ranges, "NULL argument");
   GB_REQUIRE(parts >= 1, "parts must be >= 1");
   if (g->kind != GB_KIND_DIRECTED) return gb::fail(GB_ERR_UNSUPPORTED, "page rank shards need a directed graph");
   gb::DeviceGuard guard(g->device);
   std::lock_guard<std::mutex> lock(g->mu);
-  return gb::shard_partition(g, parts, row_cost, ranges);
+  return gb::shard_partition(g, parts, row_cost, cuts, ranges);
 }
 
 gb_status gb_pr_shard_create(const gb_graph* g, uint32_t row_begin, uint32_t row_end, gb_pr_shard** shard) {

@@ -28,22 +28,60 @@ from . import _capi
 from ._capi import check, lib
 
 
+def rebalance_cuts(cuts, times):
+    """New cut fractions from the current ones and the measured per-rank times: the time density is
+    taken as constant inside each rank's weight interval and the cuts move (half-way, damped) to
+    where the cumulative time crosses k/P.  Pure function: every rank evaluates it on the same
+    all-gathered numbers."""
+    P = len(times)
+    t = [max(float(v), 1e-6) for v in times]
+    bounds = [0.0] + list(cuts) + [1.0]
+    total = sum(t)
+    new_cuts, acc, p = [], 0.0, 0
+    for k in range(1, P):
+        target = total * k / P
+        while p < P - 1 and acc + t[p] < target:
+            acc += t[p]
+            p += 1
+        frac = (target - acc) / t[p]
+        new_cuts.append(bounds[p] + min(max(frac, 0.0), 1.0) * (bounds[p + 1] - bounds[p]))
+    out = [0.5 * a + 0.5 * b for a, b in zip(cuts, new_cuts)]
+    eps = 1e-6
+    for k in range(P - 1):
+        lo = (out[k - 1] + eps) if k else eps
+        out[k] = min(max(out[k], lo), 1.0 - (P - 1 - k) * eps)
+    return out
+
+
 class CudaShardBackend:
     """The product backend: gb_pr_shard_* of libgraph_b200.so on this rank's GPU."""
 
     def __init__(self, graph, rank: int, world: int, row_cost: int = 3):
         self.graph = graph
+        self.rank, self.world, self.row_cost = rank, world, row_cost
         self.n = graph.node_count()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        ranges = np.zeros(world + 1, np.uint32)
-        check(lib.gb_pr_shard_partition(graph._g, world, row_cost, ranges.ctypes.data_as(C.c_void_p)))
-        self.ranges = [int(v) for v in ranges]
         self._shard = C.c_void_p()
-        check(lib.gb_pr_shard_create(graph._g, self.ranges[rank], self.ranges[rank + 1], C.byref(self._shard)))
+        self.launches = 0
+        self.repartition(None)
+
+    def repartition(self, cuts):
+        """(Re)builds this rank's shard; cuts = None (greedy rule) or world-1 weight fractions."""
+        ranges = np.zeros(self.world + 1, np.uint32)
+        carr = None
+        if cuts is not None:
+            carr = (C.c_double * (self.world - 1))(*[float(c) for c in cuts])
+        check(lib.gb_pr_shard_partition(self.graph._g, self.world, self.row_cost, carr,
+                                        ranges.ctypes.data_as(C.c_void_p)))
+        self.ranges = [int(v) for v in ranges]
+        if self._shard:
+            check(lib.gb_pr_shard_free(self._shard))
+            self._shard = C.c_void_p()
+        check(lib.gb_pr_shard_create(self.graph._g, self.ranges[self.rank], self.ranges[self.rank + 1],
+                                     C.byref(self._shard)))
         rb, re, act = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
         check(lib.gb_pr_shard_info(self._shard, C.byref(rb), C.byref(re), C.byref(act), None))
         self.n_active = int(act.value)
-        self.launches = 0
 
     def __del__(self):
         sh, self._shard = getattr(self, "_shard", None), None
@@ -183,6 +221,33 @@ class ShardedPageRank:
         if not tolerance > 0.0:
             self.error = float(self.err.item())
         return self
+
+    def calibrate(self, rounds: int = 2, sweeps: int = 5, damping: float = 0.85):
+        """Measured-time rebalancing (setup, untimed): run a few sweeps, all-gather every rank's mean
+        kernel time, treat the time density as constant inside each rank's current weight interval and
+        move the cut points to where the cumulative time crosses k/P.  Every rank computes the same
+        cuts from the same gathered numbers, so no rank can disagree about the new ranges."""
+        if self.world == 1 or not hasattr(self.backend, "repartition"):
+            return None
+        P = self.world
+        cuts = [k / P for k in range(1, P)]
+        history = []
+        for _ in range(rounds):
+            self.diag = []
+            self.run(sweeps, damping, 0.0)
+            torch.cuda.synchronize() if self.scores.is_cuda else None
+            k_ms = [a.elapsed_time(b) for a, b, _ in self.diag][1:]  # the first sweep also patches x0
+            self.diag = None
+            mine = torch.tensor([float(np.mean(k_ms))], dtype=torch.float64, device=self.scores.device)
+            allt = [torch.zeros_like(mine) for _ in range(P)]
+            dist.all_gather(allt, mine, group=self.group)
+            t = [float(v.item()) for v in allt]
+            history.append([round(v, 4) for v in t])
+            cuts = rebalance_cuts(cuts, t)
+            self.backend.repartition(cuts)
+            self.ranges, self.n_active = self.backend.ranges, self.backend.n_active
+        self.calibration = {"cuts": [round(c, 5) for c in cuts], "kernel_ms_per_rank": history}
+        return self.calibration
 
     def diag_summary(self):
         """(mean kernel ms, mean exchange ms) per sweep of the recorded run (diagnostics only)."""

@@ -223,7 +223,9 @@ gb_status gb_in_degree_partition(const gb_graph* graph, uint32_t parts, uint32_t
  * in_degree_partition; a row also costs ~5 vector accesses and, on the fused path, one remote store
  * per peer — measured ~2 edge-equivalents without and ~18 with 7 peers (profiles/r01_multigpu_diag.txt) */
 gb_status gb_pr_shard_partition(const gb_graph* graph, uint32_t parts, uint32_t row_cost,
-                                uint32_t* ranges);
+                                const double* cuts, uint32_t* ranges);
+/* cuts == NULL: the greedy rule above.  Otherwise parts-1 increasing fractions in (0,1) of the total
+ * weight at which the ranges are cut (measured-time rebalancing). */
 gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t row_begin, uint32_t row_end,
                              gb_pr_shard** shard);
 gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32_t* row_end,

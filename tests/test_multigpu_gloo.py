@@ -111,3 +111,27 @@ def test_sharded_page_rank_two_ranks_gloo():
 
 
 _free_port_shared = _free_port()
+
+
+def test_rebalance_cuts_pure():
+    from graph_b200.multigpu import rebalance_cuts
+    # balanced times: cuts stay put
+    c = rebalance_cuts([0.25, 0.5, 0.75], [1.0, 1.0, 1.0, 1.0])
+    assert np.allclose(c, [0.25, 0.5, 0.75])
+    # the last rank is the straggler: every cut moves right (its interval shrinks), damped by 1/2
+    c = rebalance_cuts([0.25, 0.5, 0.75], [1.0, 1.0, 1.0, 3.0])
+    assert all(b > a for a, b in zip([0.25, 0.5, 0.75], c)) and c == sorted(c) and c[-1] < 1.0
+    # exact for a piecewise-constant density when applied without damping twice the step
+    full = [2 * n - o for n, o in zip(c, [0.25, 0.5, 0.75])]
+    dens = [1 / 0.25, 1 / 0.25, 1 / 0.25, 3 / 0.25]
+    bounds = [0.0] + full + [1.0]
+    seg_time = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        tt, edges = 0.0, [0.0, 0.25, 0.5, 0.75, 1.0]
+        for d, (a, b) in zip(dens, zip(edges[:-1], edges[1:])):
+            tt += d * max(0.0, min(hi, b) - max(lo, a))
+        seg_time.append(tt)
+    assert np.allclose(seg_time, [1.5] * 4)
+    # degenerate inputs stay strictly inside (0, 1) and increasing
+    c = rebalance_cuts([0.1, 0.2, 0.3], [0.0, 0.0, 0.0, 5.0])
+    assert 0 < c[0] < c[1] < c[2] < 1
