@@ -374,7 +374,8 @@ def run_multi(args):
             "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {**workload_config(scale, world), "exchange": spr.exchange},
+            "data": "synthetic", "config": {**workload_config(scale, world), "exchange": spr.exchange,
+                                            "shard_rows": spr.ranges, "calibration": calibration},
             "clocks": clocks.summary(),
             "e2e": {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 32,
                     "d2h_bytes_per_step": int(4 * n), "steps": e2e_steps,
