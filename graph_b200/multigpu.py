@@ -73,12 +73,14 @@ class CudaShardBackend:
             carr = (C.c_double * (self.world - 1))(*[float(c) for c in cuts])
         check(lib.gb_pr_shard_partition(self.graph._g, self.world, self.row_cost, carr,
                                         ranges.ctypes.data_as(C.c_void_p)))
-        self.ranges = [int(v) for v in ranges]
-        if self._shard:
-            check(lib.gb_pr_shard_free(self._shard))
-            self._shard = C.c_void_p()
-        check(lib.gb_pr_shard_create(self.graph._g, self.ranges[self.rank], self.ranges[self.rank + 1],
-                                     C.byref(self._shard)))
+        new_ranges = [int(v) for v in ranges]
+        fresh = C.c_void_p()
+        check(lib.gb_pr_shard_create(self.graph._g, new_ranges[self.rank], new_ranges[self.rank + 1],
+                                     C.byref(fresh)))
+        # the old shard is released only once the new one exists (a failed rebuild keeps the old state)
+        old, self._shard, self.ranges = self._shard, fresh, new_ranges
+        if old:
+            check(lib.gb_pr_shard_free(old))
         rb, re, act = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
         check(lib.gb_pr_shard_info(self._shard, C.byref(rb), C.byref(re), C.byref(act), None))
         self.n_active = int(act.value)
@@ -232,6 +234,17 @@ class ShardedPageRank:
         P = self.world
         cuts = [k / P for k in range(1, P)]
         history = []
+        try:
+            return self._calibrate(rounds, sweeps, damping, cuts, history)
+        except Exception as exc:  # identical on every rank (same inputs): fall back to the static rule
+            self.diag = None
+            self.backend.repartition(None)
+            self.ranges, self.n_active = self.backend.ranges, self.backend.n_active
+            self.calibration = {"error": repr(exc)}
+            return self.calibration
+
+    def _calibrate(self, rounds, sweeps, damping, cuts, history):
+        P = self.world
         for _ in range(rounds):
             self.diag = []
             self.run(sweeps, damping, 0.0)
