@@ -10,13 +10,14 @@
 //   JACOBI — the throughput path (double-buffered, deterministic).  Vertices are renumbered internally
 //            by in-degree descending, then out-degree descending: hub rows come first, rows of equal
 //            length are neighbours, and the most gathered sources sit at the front of out_scores.
-//            Rows with more than 256 in-edges are cut into padded 256-edge SEGMENTS (one warp per
-//            segment: two 128-bit loads of the target stream per lane, 8 gathers, warp-shuffle sum ->
-//            one partial per segment); all other rows live in a SELL-32 layout (32 rows of (almost)
-//            equal length per slice, one lane per row, 128-bit coalesced target loads, no reduction).
-//            Both kernels mirror the first 52 K entries of out_scores in shared memory.  A finish
-//            kernel adds each hub row's partials in segment order and reduces the sweep error in a
-//            fixed order.  Vertices without in-edges are constant after the first sweep and skipped.
+//            Rows with more than 256 in-edges are cut into padded 256-edge SEGMENTS, 32 of them
+//            interleaved per slice; all other rows live in a SELL-32 layout (32 rows of (almost) equal
+//            length per slice).  In both, ONE LANE owns one segment / one row: it streams its targets
+//            with coalesced 128-bit loads, gathers 8 out_scores per step and keeps a private sum — no
+//            cross-lane reduction anywhere.  Both kernels mirror the first 32 K entries of out_scores
+//            in shared memory (more would starve L1 of miss slots: see pr_gather).  A finish kernel
+//            adds each hub row's segment partials in order and reduces the sweep error in a fixed
+//            order.  Vertices without in-edges are constant after the first sweep and skipped.
 //
 // Algorithmic bytes per sweep: 4m (targets) + 4(n+1) (offsets) + 5*4n (out_scores read+write,
 // scores read+write, out-degree read) = 4m + 24n + 4  (BASELINE.md §3).
@@ -37,7 +38,7 @@ constexpr int PR_HOT_MAX = 52 * 1024;  // upper bound of the GB_PR_HOT experimen
 constexpr int PR_FIN_THREADS = 256;
 constexpr uint32_t PR_LONG_DEG = 256;  // rows with more in-edges are cut into segments, the rest go to SELL-32
 constexpr uint32_t PR_SEG = 256;       // edges per segment (8 per lane)
-constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;
+constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;  // sweeps bracketed by CUDA events when profiling is on
 
 // the share of a contiguous range of internal rows (the whole graph on one GPU, or one rank's shard
 // of the 1-D edge-cut) in the two layouts
