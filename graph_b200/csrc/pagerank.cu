@@ -22,7 +22,6 @@
 // Algorithmic bytes per sweep: 4m (targets) + 4(n+1) (offsets) + 5*4n (out_scores read+write,
 // scores read+write, out-degree read) = 4m + 24n + 4  (BASELINE.md §3).
 #include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -579,10 +578,13 @@ static gb_status build_range(const gb_graph* g, const PrPlan* p, uint32_t row_be
   r->row_end = row_end;
   // SELL part: rows [max(row_begin, n_long), row_end) — shard boundaries sit on slice boundaries
   const uint32_t sb = std::max(row_begin, p->n_long), se = std::max(row_end, p->n_long);
-  GB_REQUIRE((sb - p->n_long) % 32 == 0, "shard boundary %u is not on a SELL slice boundary", row_begin);
-  r->slice_begin = (sb - p->n_long) / 32;
-  r->slice_end = (se - p->n_long + 31) / 32;
+  r->slice_begin = r->slice_end = 0;
   r->sell_row_end = se;
+  if (sb < se) {  // an empty SELL share (e.g. a range that starts at n_active) needs no alignment
+    GB_REQUIRE((sb - p->n_long) % 32 == 0, "shard boundary %u is not on a SELL slice boundary", row_begin);
+    r->slice_begin = (sb - p->n_long) / 32;
+    r->slice_end = (se - p->n_long + 31) / 32;
+  }
   // hub rows of the range and their segments
   r->long_begin = std::min(row_begin, p->n_long);
   r->long_end = std::min(row_end, p->n_long);
