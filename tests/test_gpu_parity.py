@@ -429,3 +429,47 @@ def test_invalid_host_csr_is_rejected(gb):
         gb.Graph.from_csr(bad_off, np.array([1, 0], np.uint32))
     with pytest.raises(ValueError, match="out of range|>= node_count"):
         gb.DiGraph.from_numpy(np.array([[0, 9]], dtype=np.uint32), node_count=4)
+
+
+# ---- shard API on one GPU: several virtual ranks, slices exchanged by plain copies ---------------
+@pytest.mark.parametrize("world,cuts", [(2, None), (3, [0.2, 0.7]), (4, [1e-6, 0.5, 0.999999]), (8, None)])
+def test_shard_api_virtual_ranks_match_single_gpu(gb, world, cuts):
+    import torch
+    from graph_b200.multigpu import CudaShardBackend
+    g = gb.DiGraph.rmat(15, seed=11, layout=gb.Layout.Sorted)
+    n = g.node_count()
+    sweeps, damping = 6, 0.85
+    want = g.page_rank(max_iterations=sweeps, tolerance=0.0, damping_factor=damping, mode="jacobi")
+    ranks = [CudaShardBackend(g, r, world, row_cost=5) for r in range(world)]
+    if cuts is not None:
+        for b in ranks:
+            b.repartition(cuts)
+    ranges = ranks[0].ranges
+    assert all(b.ranges == ranges for b in ranks) and ranges[0] == 0 and ranges[-1] == n
+    assert all(ranges[i] <= ranges[i + 1] for i in range(world))
+    n_active = ranks[0].n_active
+    dev = ranks[0].device
+    x = [[torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(world)]
+    scores = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(world)]
+    err = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    for r, b in enumerate(ranks):
+        b.init(damping, x[r][0], x[r][1], scores[r])
+    total = 0.0
+    for sweep in range(1, sweeps + 1):
+        cur, nxt = (sweep - 1) & 1, sweep & 1
+        for r, b in enumerate(ranks):
+            b.step(damping, sweep, x[r][cur], x[r][nxt], None, scores[r], err[r])
+        torch.cuda.synchronize()
+        for r in range(world):  # the all-gather: every rank's slice goes to every other rank
+            lo, hi = min(ranges[r], n_active), min(ranges[r + 1], n_active)
+            for q in range(world):
+                if q != r and hi > lo:
+                    x[q][nxt][lo:hi].copy_(x[r][nxt][lo:hi])
+        total = sum(float(e.item()) for e in err)
+    for r in range(world):
+        lo, hi = min(ranges[r], n_active), min(ranges[r + 1], n_active)
+        if hi > lo:
+            scores[0][lo:hi].copy_(scores[r][lo:hi])
+    got = ranks[0].finish(scores[0]).cpu().numpy()
+    assert got.tobytes() == want.scores().tobytes()   # one lane per row / segment: sharding cannot change a sum
+    assert abs(total - want.error) <= 1e-9 + 1e-9 * want.error
