@@ -106,3 +106,20 @@ def test_defaults_match_reference_configs():
             gb.PageRankConfig().damping_factor) == (20, 1e-4, 0.85)  # page_rank.rs:46-48
     w = gb.WccConfig()
     assert (w.chunk_size, w.neighbor_rounds, w.sampling_size) == (16384, 2, 1024)  # wcc.rs:67-69
+
+
+def test_graph_mate_shim_exposes_the_reference_module_surface():
+    """crates/mate/graph_mate.pyi: the names the reference's tests and notebooks import."""
+    import graph_mate
+    import graph_b200
+    for name in ("DiGraph", "Graph", "Layout", "FileFormat", "PageRankResult", "WccResult", "TriangleCountResult"):
+        assert getattr(graph_mate, name) is getattr(graph_b200, name)
+    for meth in ("load", "from_numpy", "from_pandas", "node_count", "edge_count", "out_degree", "in_degree",
+                 "out_neighbors", "in_neighbors", "copy_out_neighbors", "copy_in_neighbors", "to_undirected",
+                 "page_rank", "wcc"):
+        assert callable(getattr(graph_mate.DiGraph, meth)), meth
+    for meth in ("load", "from_numpy", "from_pandas", "node_count", "edge_count", "degree", "neighbors",
+                 "copy_neighbors", "make_degree_ordered", "global_triangle_count"):
+        assert callable(getattr(graph_mate.Graph, meth)), meth
+    assert {graph_mate.Layout.Sorted.name, graph_mate.Layout.Unsorted.name, graph_mate.Layout.Deduplicated.name} == \
+        {"Sorted", "Unsorted", "Deduplicated"}
