@@ -133,11 +133,6 @@ __global__ void k_expand_rows(const uint32_t* __restrict__ off, uint32_t n, uint
   (void)count;
 }
 
-__global__ void k_degrees(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ deg) {
-  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
-    deg[v] = off[v + 1] - off[v];
-}
-
 __global__ void k_check_ids(const uint32_t* __restrict__ a, uint64_t count, uint32_t n,
                             unsigned int* __restrict__ bad) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
