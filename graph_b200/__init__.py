@@ -148,33 +148,29 @@ class SsspResult:
 
 
 # ---- input files (crates/builder/src/input/{graph500,edgelist}.rs) --------------------------------
+# parsed by the library's native multi-threaded readers (csrc/io.cu)
 def _read_graph500(path) -> tuple[np.ndarray, np.ndarray, int]:
     """Packed 12-byte edges {v0_low, v1_low, high} (graph500.rs:111-127); node_count = edges/16 (:74)."""
-    raw = np.fromfile(path, dtype="<u4")
-    m = raw.size // 3
-    rec = raw[: 3 * m].reshape(m, 3)
-    high = rec[:, 2]
-    if m and ((high & 0xFFFF).any() or (high >> 16).any()):
-        raise ValueError("Graph500 node id does not fit 32 bits")  # Idx::new assert, index.rs:51-54
-    return np.ascontiguousarray(rec[:, 0]), np.ascontiguousarray(rec[:, 1]), m // 16
+    raw = np.fromfile(path, dtype=np.uint8)
+    m = raw.size // 12
+    src = np.empty(m, np.uint32)
+    dst = np.empty(m, np.uint32)
+    got, n = C.c_uint64(0), C.c_uint32(0)
+    check(lib.gb_graph500_decode(_ptr(raw) if raw.size else None, raw.size, _ptr(src), _ptr(dst), C.byref(got),
+                                 C.byref(n)))
+    return src, dst, int(n.value)
 
 
 def _read_edge_list(path, with_values=False):
     """Text lines `<src> <dst>[ <value>]` with \\n or \\r\\n endings (edgelist.rs:181-279)."""
     text = Path(path).read_bytes()
-    tokens = text.split()
-    first_line = text.split(b"\n", 1)[0].split()
-    cols = max(len(first_line), 2)
-    arr = np.array(tokens).reshape(-1, cols) if tokens else np.empty((0, cols), dtype="S1")
-    src = arr[:, 0].astype(np.uint64)
-    dst = arr[:, 1].astype(np.uint64)
-    if src.size and max(src.max(), dst.max()) > 0xFFFFFFFF:
-        raise ValueError("edge list node id does not fit 32 bits")
-    src, dst = src.astype(np.uint32), dst.astype(np.uint32)
-    if with_values:
-        w = arr[:, 2].astype(np.float32) if cols > 2 else np.zeros(len(src), np.float32)
-        return src, dst, w
-    return src, dst
+    m = C.c_uint64(0)
+    check(lib.gb_edge_list_parse(text, len(text), None, None, None, C.byref(m)))
+    src = np.empty(m.value, np.uint32)
+    dst = np.empty(m.value, np.uint32)
+    w = np.empty(m.value, np.float32) if with_values else None
+    check(lib.gb_edge_list_parse(text, len(text), _ptr(src), _ptr(dst), _ptr(w), C.byref(m)))
+    return (src, dst, w) if with_values else (src, dst)
 
 
 def _edges_from_numpy(arr) -> tuple[np.ndarray, np.ndarray]:

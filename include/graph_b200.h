@@ -156,6 +156,17 @@ gb_status gb_graph_rmat(int device, uint32_t scale, uint32_t edge_factor, uint64
 gb_status gb_rmat_edges(int device, uint32_t scale, uint64_t seed, uint64_t first, uint64_t count,
                         uint32_t* src, uint32_t* dst);
 
+/* ---- input formats (host side, multi-threaded) ------------------------------------------------
+ * Graph500 packed 12-byte edges (input/graph500.rs:63-127): src/dst hold len/12 entries;
+ * node_count = edge_count / 16 (graph500.rs:74).  Ids above 32 bits are an error. */
+gb_status gb_graph500_decode(const void* bytes, uint64_t len, uint32_t* src, uint32_t* dst,
+                             uint64_t* edge_count, uint32_t* node_count);
+/* Text edge list "<src> <dst>[ <f32>]" with \n or \r\n line ends (input/edgelist.rs:181-279).
+ * Call with src == NULL to obtain *edge_count, then again with arrays of that size; values may be
+ * NULL.  Edges come out in file order. */
+gb_status gb_edge_list_parse(const char* text, uint64_t len, uint32_t* src, uint32_t* dst,
+                             float* values, uint64_t* edge_count);
+
 gb_status gb_graph_free(gb_graph* graph);
 gb_status gb_graph_get_info(const gb_graph* graph, gb_graph_info* info);
 /* copy a CSR back to the host (neighbour views of the host mirror: csr.rs:97-117).

@@ -12,6 +12,8 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <fstream>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -37,6 +39,9 @@ namespace prelude {
 
 // crates/builder/src/graph/csr.rs:35-45
 enum class CsrLayout { Unsorted = GB_LAYOUT_UNSORTED, Sorted = GB_LAYOUT_SORTED, Deduplicated = GB_LAYOUT_DEDUPLICATED };
+
+// input formats of `GraphBuilder::file_format(..).path(..)` (builder.rs:283-361; input/graph500.rs, input/edgelist.rs)
+enum class FileFormat { Graph500, EdgeList };
 
 // crates/algos/src/page_rank.rs:14-56
 struct PageRankConfig {
@@ -176,6 +181,32 @@ class GraphBuilder {
     return *this;
   }
   GraphBuilder& node_count(std::uint32_t n) { n_ = n; return *this; }
+  // file_format(format).path(p): read the file with the library's native readers (csrc/io.cu)
+  GraphBuilder& file_format(FileFormat f) { format_ = f; return *this; }
+  GraphBuilder& path(const std::string& p) {
+    std::ifstream in(p, std::ios::binary);
+    if (!in) throw Error(GB_ERR_INVALID, "cannot open " + p);  // Error::IoError, lib.rs:276-281
+    std::vector<char> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    std::uint64_t m = 0;
+    w_.clear();
+    if (format_ == FileFormat::Graph500) {
+      src_.resize(bytes.size() / 12);
+      dst_.resize(bytes.size() / 12);
+      detail::check(gb_graph500_decode(bytes.data(), bytes.size(), src_.data(), dst_.data(), &m, &n_));
+    } else {
+      detail::check(gb_edge_list_parse(bytes.data(), bytes.size(), nullptr, nullptr, nullptr, &m));
+      src_.resize(m);
+      dst_.resize(m);
+      detail::check(gb_edge_list_parse(bytes.data(), bytes.size(), src_.data(), dst_.data(), nullptr, &m));
+      n_ = 0;  // max id + 1
+    }
+    return *this;
+  }
+  // what the builder currently holds (after edges(..) or path(..))
+  std::size_t pending_edge_count() const { return src_.size(); }
+  std::uint32_t pending_node_count() const { return n_; }  // 0 = "max id + 1" at build time
+  const std::vector<std::uint32_t>& pending_sources() const { return src_; }
+  const std::vector<std::uint32_t>& pending_targets() const { return dst_; }
   DirectedCsrGraph build_directed() const {
     gb_graph* g = nullptr;
     detail::check(gb_digraph_from_edges_u32(device_, src_.data(), dst_.data(), w_.empty() ? nullptr : w_.data(), src_.size(), n_,
@@ -190,6 +221,7 @@ class GraphBuilder {
 
  private:
   CsrLayout layout_ = CsrLayout::Unsorted;  // CsrLayout::default()
+  FileFormat format_ = FileFormat::EdgeList;
   int device_ = 0;
   std::uint32_t n_ = 0;
   std::vector<std::uint32_t> src_, dst_;

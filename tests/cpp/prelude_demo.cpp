@@ -17,7 +17,7 @@ using namespace graph::prelude;
     }                                                             \
   } while (0)
 
-int main() {
+int main(int argc, char** argv) {
   try {
     {  // page_rank doc-test, lib.rs:96-140
       DirectedCsrGraph g = GraphBuilder()
@@ -69,6 +69,18 @@ int main() {
       const std::uint32_t n0[5] = {1, 1, 2, 2, 3};
       auto r = g.neighbors(0);
       EXPECT(r.second - r.first == 5 && std::memcmp(r.first, n0, sizeof n0) == 0);
+    }
+    if (argc > 1) {  // builder.rs doc-tests: file inputs (argv[1] = directory with the reference's fixtures)
+      const std::string dir = argv[1];
+      DirectedCsrGraph g = GraphBuilder().csr_layout(CsrLayout::Sorted).file_format(FileFormat::Graph500)
+                               .path(dir + "/scale_8.graph500").build_directed();
+      EXPECT(g.node_count() == 256 && g.edge_count() == 4096);   // crates/builder/tests/builder.rs:449-468
+      auto o = g.out_neighbors(0);
+      EXPECT(o.second - o.first == 2 && o.first[0] == 37 && o.first[1] == 157);
+      UndirectedCsrGraph u = GraphBuilder().csr_layout(CsrLayout::Sorted).file_format(FileFormat::EdgeList)
+                                 .path(dir + "/test.el").build_undirected();
+      EXPECT(u.node_count() == 5 && u.edge_count() == 6 && u.degree(1) == 3);   // builder.rs:534-564
+      relabel_graph(u);
     }
     {  // errors instead of panics
       DirectedCsrGraph g = GraphBuilder().edges({{0, 1}}).build_directed();

@@ -8,13 +8,20 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def build_demo(tmp_path):
-    exe = tmp_path / "prelude_demo"
+def build_demo(tmp_path, name="prelude_demo"):
+    exe = tmp_path / name
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
-           str(ROOT / "tests" / "cpp" / "prelude_demo.cpp"), "-o", str(exe), f"-L{ROOT / 'graph_b200'}",
+           str(ROOT / "tests" / "cpp" / f"{name}.cpp"), "-o", str(exe), f"-L{ROOT / 'graph_b200'}",
            "-lgraph_b200", f"-Wl,-rpath,{ROOT / 'graph_b200'}"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return exe
+
+
+def test_graph_builder_reads_the_reference_fixtures(tmp_path):
+    """GraphBuilder().file_format(..).path(..) through the native readers — no device involved."""
+    exe = build_demo(tmp_path, "builder_io")
+    r = subprocess.run([str(exe), str(ROOT / "tests" / "golden")], capture_output=True, text=True)
+    assert r.returncode == 0 and "builder_io ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_prelude_header_compiles_and_links(tmp_path):
@@ -30,6 +37,6 @@ def test_prelude_header_compiles_and_links(tmp_path):
 @pytest.mark.gpu
 def test_prelude_demo_reproduces_reference_goldens(tmp_path):
     exe = build_demo(tmp_path)
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(ROOT / "tests" / "golden")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "prelude_demo ok" in r.stdout

@@ -123,3 +123,44 @@ def test_graph_mate_shim_exposes_the_reference_module_surface():
         assert callable(getattr(graph_mate.Graph, meth)), meth
     assert {graph_mate.Layout.Sorted.name, graph_mate.Layout.Unsorted.name, graph_mate.Layout.Deduplicated.name} == \
         {"Sorted", "Unsorted", "Deduplicated"}
+
+
+def test_native_readers_match_oracle_on_large_inputs(tmp_path):
+    """csrc/io.cu (multi-threaded, chunked at line boundaries) against the oracle's single-threaded
+    restatement of input/graph500.rs and input/edgelist.rs, on inputs large enough for many chunks."""
+    import graph_b200 as gb
+    import oracle
+    rng = np.random.default_rng(5)
+    m = 600_000
+    src = rng.integers(0, 1 << 20, m).astype(np.uint32)
+    dst = rng.integers(0, 1 << 20, m).astype(np.uint32)
+    # Graph500 packed records
+    rec = np.zeros((m, 3), dtype="<u4")
+    rec[:, 0], rec[:, 1] = src, dst
+    p = tmp_path / "g.graph500"
+    rec.tofile(p)
+    s, d, n = gb._read_graph500(p)
+    os_, od, on = oracle.graph500_decode(p.read_bytes())
+    assert n == on == m // 16 and (s == os_).all() and (d == od).all() and (s == src).all()
+    # text edge lists: plain, CRLF, weighted, and a last line without newline
+    w = (rng.integers(0, 1 << 16, m) / 256.0).astype(np.float32)
+    plain = "".join(f"{a} {b}\n" for a, b in zip(src.tolist(), dst.tolist()))
+    crlf = plain.replace("\n", "\r\n")
+    weighted = "".join(f"{a} {b} {c}\n" for a, b, c in zip(src.tolist(), dst.tolist(), w.tolist()))
+    for name, text, vals in (("plain", plain, False), ("crlf", crlf, False), ("weighted", weighted, True),
+                             ("no_trailing_newline", plain[:-1], False)):
+        f = tmp_path / f"{name}.el"
+        f.write_text(text)
+        got = gb._read_edge_list(f, with_values=vals)
+        want = oracle.edgelist_parse(text.encode(), with_values=vals)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[0] == src).all(), name
+        if vals:
+            assert (got[2] == want[2]).all() and (got[2] == w).all()
+    # ids above 32 bits are rejected like Idx::new (index.rs:51-54)
+    f = tmp_path / "big.el"
+    f.write_text("1 2\n4294967296 3\n")
+    with pytest.raises(ValueError, match="32 bits"):
+        gb._read_edge_list(f)
+    (tmp_path / "empty.el").write_text("")
+    e = gb._read_edge_list(tmp_path / "empty.el")
+    assert len(e[0]) == 0
