@@ -20,7 +20,7 @@ from ._capi import GraphB200Error, check, lib
 
 __all__ = ["DiGraph", "Graph", "Layout", "FileFormat", "PageRankResult", "WccResult",
            "TriangleCountResult", "SsspResult", "PageRankConfig", "WccConfig", "DeltaSteppingConfig",
-           "GraphB200Error", "device_count", "set_device"]
+           "GraphB200Error", "device_count", "set_device", "write_graph500"]
 
 _device = 0
 
@@ -159,6 +159,18 @@ def _read_graph500(path) -> tuple[np.ndarray, np.ndarray, int]:
     check(lib.gb_graph500_decode(_ptr(raw) if raw.size else None, raw.size, _ptr(src), _ptr(dst), C.byref(got),
                                  C.byref(n)))
     return src, dst, int(n.value)
+
+
+def write_graph500(path, src, dst) -> None:
+    """Writes edges as the packed Graph500 file the reference reads (`app -f graph500 --use-32-bit`,
+    `DiGraph.load(path)`); the reader derives node_count = edge_count / 16 (graph500.rs:74)."""
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    dst = np.ascontiguousarray(dst, dtype=np.uint32)
+    if len(src) != len(dst):
+        raise ValueError("src and dst must have the same length")
+    raw = np.empty(12 * len(src), np.uint8)
+    check(lib.gb_graph500_encode(_ptr(src), _ptr(dst), len(src), _ptr(raw)))
+    raw.tofile(path)
 
 
 def _read_edge_list(path, with_values=False):

@@ -86,6 +86,23 @@ gb_status gb_graph500_decode(const void* bytes, uint64_t len, uint32_t* src, uin
   return GB_OK;
 }
 
+// The inverse: edges -> packed 12-byte records (high word 0 for 32-bit ids), the file format the
+// reference's CLI reads with `-f graph500 --use-32-bit` (crates/app/src/runner.rs:104-133).
+gb_status gb_graph500_encode(const uint32_t* src, const uint32_t* dst, uint64_t edge_count, void* bytes) {
+  if (edge_count == 0) return GB_OK;
+  GB_REQUIRE(src && dst && bytes, "NULL argument");
+  const unsigned T = gb::io_threads(edge_count);
+  uint8_t* base = static_cast<uint8_t*>(bytes);
+  gb::parallel_chunks(T, [&](unsigned t) {
+    const uint64_t b = edge_count * t / T, e = edge_count * (t + 1) / T;
+    for (uint64_t i = b; i < e; ++i) {
+      const uint32_t rec[3] = {src[i], dst[i], 0u};
+      std::memcpy(base + 12 * i, rec, 12);
+    }
+  });
+  return GB_OK;
+}
+
 // Two-phase use: call with src == NULL to obtain *edge_count, allocate, call again to fill.
 // values may be NULL.  Ids above 32 bits are an error.
 gb_status gb_edge_list_parse(const char* text, uint64_t len, uint32_t* src, uint32_t* dst, float* values,

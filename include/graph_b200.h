@@ -161,6 +161,9 @@ gb_status gb_rmat_edges(int device, uint32_t scale, uint64_t seed, uint64_t firs
  * node_count = edge_count / 16 (graph500.rs:74).  Ids above 32 bits are an error. */
 gb_status gb_graph500_decode(const void* bytes, uint64_t len, uint32_t* src, uint32_t* dst,
                              uint64_t* edge_count, uint32_t* node_count);
+/* edges -> packed records (12 * edge_count bytes): the file the reference's CLI reads with
+ * `-f graph500 --use-32-bit` (crates/app/src/runner.rs:104-133); note its node_count = edges/16 rule */
+gb_status gb_graph500_encode(const uint32_t* src, const uint32_t* dst, uint64_t edge_count, void* bytes);
 /* Text edge list "<src> <dst>[ <f32>]" with \n or \r\n line ends (input/edgelist.rs:181-279).
  * Call with src == NULL to obtain *edge_count, then again with arrays of that size; values may be
  * NULL.  Edges come out in file order. */

@@ -164,3 +164,17 @@ def test_native_readers_match_oracle_on_large_inputs(tmp_path):
     (tmp_path / "empty.el").write_text("")
     e = gb._read_edge_list(tmp_path / "empty.el")
     assert len(e[0]) == 0
+
+
+def test_graph500_writer_round_trips_through_both_readers(tmp_path):
+    import graph_b200 as gb
+    import oracle
+    src, dst = oracle.rmat_edges(12, seed=3)           # 65536 edges, 4096 nodes = edges / 16
+    p = tmp_path / "rmat12.graph500"
+    gb.write_graph500(p, src, dst)
+    assert p.stat().st_size == 12 * len(src)
+    s, d, n = gb._read_graph500(p)
+    os_, od, on = oracle.graph500_decode(p.read_bytes())
+    assert n == on == 4096 and (s == src).all() and (d == dst).all() and (os_ == src).all() and (od == dst).all()
+    with pytest.raises(ValueError):
+        gb.write_graph500(p, src, dst[:-1])
