@@ -11,7 +11,7 @@ quoted on; it fits one B200).  One JSON line is printed by rank 0.
   e2e          same metric through the C ABI with HOST buffers (gb_page_rank_csr_u32): every step uploads
                the pinned host in-CSR + out offsets, builds the device layout, runs page_rank and
                copies the ranks back; nothing stays resident between steps
-  roofline     the sweep kernels (k_pr_seg + k_pr_sell) timed with CUDA events around every sweep:
+  roofline     the sweep kernels (k_pr_cb + k_pr_sell + k_pr_finish) timed with CUDA events around every sweep:
                algorithmic bytes (4m + 24n + 4 per sweep) / mean launch time vs measured HBM peak
   cpu_baseline the reference's multi-threaded in-place sweep (oracle.page_rank_mt, the C restatement
                of crates/algos/src/page_rank.rs:113-168) on the same graph, bounded sample
@@ -35,6 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 SWEEPS = 20
+PR_KERNEL_VERSION = "r02-cb1"   # bump with every change of the sweep kernels / layout (keys profiles/pr_traffic.json)
 DAMPING = 0.85
 SEED = 42
 EDGE_FACTOR = 16
@@ -135,6 +136,37 @@ def cpu_leg(out_off, in_off, in_tgt, n, m, sweeps, threads=0):
     return m * it / dt / 1e9, dt, oracle.hardware_threads() if threads == 0 else threads
 
 
+def verify_last_sweep(g, d_scores, in_off, in_tgt, out_off, n, samples=4096, rtol=1e-6):
+    """Untimed check of the benchmarked result: sweep 20 of sampled rows is re-evaluated in f64 on the
+    host from the out_scores of a 19-sweep run (deterministic, so its scores are sweep 20's inputs).
+    d_scores holds the 20-sweep ranks of the timed runs."""
+    import torch
+    from graph_b200 import _capi
+    from graph_b200._capi import lib, check
+    s20 = d_scores.cpu().numpy()
+    it, err = C.c_uint64(0), C.c_double(0.0)
+    cfg19 = _capi.PageRankConfig(SWEEPS - 1, 0.0, DAMPING, _capi.PR_JACOBI)
+    d19 = torch.empty(n, dtype=torch.float32, device="cuda")
+    check(lib.gb_page_rank_device(g._g, C.byref(cfg19), C.c_void_p(d19.data_ptr()), C.byref(it), C.byref(err)))
+    s19 = d19.cpu().numpy()
+    outdeg = np.diff(out_off.astype(np.int64)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        x19 = s19 / outdeg                       # f32 IEEE division, as the kernel's __fdiv_rn
+    indeg = np.diff(in_off.astype(np.int64))
+    rng = np.random.default_rng(7)
+    rows = np.unique(np.concatenate([rng.integers(0, n, samples), np.argpartition(indeg, -64)[-64:]]))
+    base = (np.float32(1.0) - np.float32(DAMPING)) / np.float32(n)
+    worst = 0.0
+    for u in rows:
+        tot = np.float32(x19[in_tgt[in_off[u]:in_off[u + 1]]].astype(np.float64).sum())
+        want = np.float32(base + np.float32(np.float32(DAMPING) * tot))
+        worst = max(worst, abs(float(s20[u]) - float(want)) / float(want))
+    ok = bool(worst <= rtol and np.isfinite(s20).all())
+    return ok, {"rows": int(len(rows)), "max_rel_err": worst, "rtol": rtol,
+                "what": "sweep 20 of sampled rows (random + the 64 largest hubs) re-evaluated in f64 on the host "
+                        "from a 19-sweep run's out_scores"}
+
+
 def host_csr_from_device(g, pinned=True):
     """(out_off, out_tgt, in_off, in_tgt) host copies of a DiGraph's CSR pair, pinned when possible."""
     from graph_b200._capi import lib, check, CSR_OUT, CSR_IN
@@ -187,7 +219,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(scale, 0),
         "cpu_baseline": {"value": gteps, "unit": "GTEPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gteps, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,20 +285,27 @@ def run_single(args):
     peak, peak_src = peaks()
     bytes_per_launch = algorithmic_bytes(n, m)
     achieved = bytes_per_launch / (hot_ms / hot_n * 1e-3) / 1e9 if hot_n else 0.0
-    traffic = None
-    tp = ROOT / "profiles" / "pr_pull_traffic.json"
+    # DRAM bytes per sweep from the committed ncu capture of THIS kernel version and layout (else null)
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "pr_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(f"scale{scale}")
+            rec = json.loads(tp.read_text())
+            if rec.get("kernel_version") == PR_KERNEL_VERSION:
+                traffic = rec.get(f"scale{scale}")
+                traffic_src = rec.get("source")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_pr_seg + k_pr_sell (one sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "k_pr_cb + k_pr_sell + k_pr_finish (one sweep)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": hot_ms / max(hot_n, 1),
                 "kernel_share_of_step": (hot_ms / max(min(args.steps, 3), 1)) / (ms / args.steps)}
 
+    layout = g.page_rank_plan_info()
     # e2e through the C ABI with host buffers (pinned): upload + device twin + page_rank + ranks back
     (out_off, out_tgt, in_off, in_tgt), keep = host_csr_from_device(g)
+    verified, verification = verify_last_sweep(g, d_scores, in_off, in_tgt, out_off, n)
     del g
     torch.cuda.empty_cache()
     _, h_scores = pinned_empty(n, np.float32)
@@ -303,8 +342,9 @@ def run_single(args):
     line = {
         "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(scale, 1), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {**workload_config(scale, 1), "layout": layout}, "clocks": clocks.summary(), "e2e": e2e,
+        "gpu_launches": int(launches), "verified": verified, "verification": verification,
         "roofline": roofline, "cpu_baseline": cpu,
         "hbm_roofline_gteps": peak * 1e9 / (bytes_per_launch / m) / 1e9,
         "frac_of_hbm_roofline_whole_step": (bytes_per_launch * SWEEPS * args.steps / (ms * 1e-3) / 1e9) / peak,
@@ -327,10 +367,7 @@ def run_multi(args):
     scale, n = args.scale, 1 << args.scale
     m = EDGE_FACTOR * n
     g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
-    spr = ShardedPageRank(g, exchange=args.exchange)
-    calibration = None
-    if not args.no_calibrate:
-        calibration = spr.calibrate()  # setup (like the layout build): measured-time shard rebalancing
+    spr = ShardedPageRank(g, exchange=args.exchange, multicast=not args.no_multicast)
     for _ in range(max(args.warmup, 3)):
         spr.run(SWEEPS, DAMPING)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,7 +399,7 @@ def run_multi(args):
         spr.diag = []
         spr.run(SWEEPS, DAMPING)
         k_ms, x_ms = spr.diag_summary()
-        info = torch.tensor([k_ms, x_ms, float(spr.ranges[rank + 1] - spr.ranges[rank])], device="cuda", dtype=torch.float64)
+        info = torch.tensor([k_ms, x_ms, float(spr.backend.stats["local_rows"])], device="cuda", dtype=torch.float64)
         allinfo = [torch.zeros_like(info) for _ in range(world)]
         dist.all_gather(allinfo, info)
         if rank == 0:
@@ -376,13 +413,14 @@ def run_multi(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {**workload_config(scale, world), "exchange": spr.exchange,
-                                            "shard_rows": spr.ranges, "calibration": calibration},
+                                            "multicast": spr.multicast, "deal": "32-row slices round-robin",
+                                            "layout_rank0": spr.backend.stats},
             "clocks": clocks.summary(),
             "e2e": {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 32,
                     "d2h_bytes_per_step": int(4 * n), "steps": e2e_steps,
                     "what": "sharded page_rank on resident shards + all ranks' scores copied to the host"},
             "gpu_launches": int(spr.launches),
-            "roofline": {"bound": "hbm", "kernel": "k_pr_seg + k_pr_sell (one sweep)", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_pr_cb + k_pr_sell + k_pr_finish (one sweep)", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs, whole step incl. exchange"},
             "cpu_baseline": None,
@@ -399,10 +437,10 @@ def main():
     ap.add_argument("--scale", type=int, default=26)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sweeps", type=int, default=3, help="sweeps of the CPU baseline sample")
-    ap.add_argument("--ref-sweeps", type=int, default=2, help="sweeps per step of --impl reference")
+    ap.add_argument("--ref-sweeps", type=int, default=5, help="sweeps per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl", "allgather"])
-    ap.add_argument("--no-calibrate", action="store_true", help="multi-GPU: keep the static shard partition")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "allgather"])
+    ap.add_argument("--no-multicast", action="store_true", help="multi-GPU: unicast peer stores instead of multimem.st")
     ap.add_argument("--diag", action="store_true", help="multi-GPU: print per-rank kernel / exchange ms per sweep")
     args = ap.parse_args()
     if args.impl == "reference":

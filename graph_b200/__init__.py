@@ -416,6 +416,12 @@ class DiGraph(_Handle):
         out = [(int(r[i]), int(r[i + 1])) for i in range(parts) if r[i + 1] > r[i]]
         return out
 
+    def page_rank_plan_info(self) -> dict:
+        """Statistics of the device layout the JACOBI page_rank sweeps (built on first use)."""
+        st = _capi.PrShardStats()
+        check(lib.gb_page_rank_plan_info(self._g, C.byref(st)))
+        return st.as_dict()
+
     # -- algorithms --
     def page_rank(self, *, max_iterations: int = PageRankConfig.DEFAULT_MAX_ITERATIONS,
                   tolerance: float = PageRankConfig.DEFAULT_TOLERANCE,

@@ -40,6 +40,18 @@ class Timing(C.Structure):
                 ("hot_kernel_launches", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class PrShardStats(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("active_rows", C.c_uint32),
+                ("local_rows", C.c_uint32), ("local_edges", C.c_uint64), ("block_edges", C.c_uint64),
+                ("block_entries", C.c_uint32), ("hot_blocks", C.c_uint32), ("segments", C.c_uint64),
+                ("groups", C.c_uint64), ("chunks", C.c_uint32), ("tasks", C.c_uint32),
+                ("cut_segments", C.c_uint32), ("chunk_groups", C.c_uint32),
+                ("launches_per_sweep", C.c_uint32), ("device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
 class GraphB200Error(RuntimeError):
     """CUDA / allocation failure inside libgraph_b200."""
 
@@ -82,11 +94,12 @@ SIGNATURES = {
     "gb_sssp_device": (C.c_int, [_P, C.POINTER(SsspConfig), _P]),
     "gb_triangle_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gb_in_degree_partition": (C.c_int, [_P, C.c_uint32, _P]),
-    "gb_pr_shard_partition": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
+    "gb_page_rank_plan_info": (C.c_int, [_P, C.POINTER(PrShardStats)]),
+    "gb_page_rank_plan_reset": (C.c_int, [_P]),
     "gb_pr_shard_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
-    "gb_pr_shard_info": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gb_pr_shard_info": (C.c_int, [_P, C.POINTER(PrShardStats)]),
     "gb_pr_shard_init": (C.c_int, [_P, C.c_float, _P, _P, _P, _P]),
-    "gb_pr_shard_step": (C.c_int, [_P, C.c_float, C.c_uint64, _P, _P, _P, C.c_uint32, _P, _P, _P]),
+    "gb_pr_shard_step": (C.c_int, [_P, C.c_float, C.c_uint64, _P, _P, _P, C.c_uint32, _P, _P, _P, _P]),
     "gb_pr_shard_finish": (C.c_int, [_P, _P, _P, _P]),
     "gb_pr_shard_free": (C.c_int, [_P]),
 }

@@ -7,24 +7,37 @@
 //            multiply/add (no FMA), IEEE division.  One warp walks the vertices in id order; lanes
 //            only parallelise the gather loads, the additions stay sequential.  Bit-exact with the
 //            reference wherever the reference is deterministic (n <= 16384 = one chunk).
-//   JACOBI — the throughput path (double-buffered, deterministic).  Vertices are renumbered internally
-//            by in-degree descending, then out-degree descending: hub rows come first, rows of equal
-//            length are neighbours, and the most gathered sources sit at the front of out_scores.
-//            Rows with more than 256 in-edges are cut into padded 256-edge SEGMENTS, 32 of them
-//            interleaved per slice; all other rows live in a SELL-32 layout (32 rows of (almost) equal
-//            length per slice).  In both, ONE LANE owns one segment / one row: it streams its targets
-//            with coalesced 128-bit loads, gathers 8 out_scores per step and keeps a private sum — no
-//            cross-lane reduction anywhere.  Both kernels mirror the first 32 K entries of out_scores
-//            in shared memory (more would starve L1 of miss slots: see pr_gather).  A finish kernel
-//            adds each hub row's segment partials in order and reduces the sweep error in a fixed
-//            order.  Vertices without in-edges are constant after the first sweep and skipped.
+//   JACOBI — the throughput path (double-buffered, deterministic).
+//
+// JACOBI design (round 2).  A pull sweep issues one 4-byte gather per edge, and divergent gathers
+// that miss L1 are limited to ~1 per clock per SM by the L1TEX->XBAR request port
+// (profiles/r01_gather_ceiling_microbench.txt) — 27 % of the HBM roofline, whatever the layout of the
+// index stream.  Shared memory serves ~9 random 4-byte reads per clock.  So the sweep is COLUMN
+// BLOCKED: vertices are renumbered by in-degree descending, then out-degree descending (hot sources
+// first); the source vector is cut into blocks of B entries that fit in shared memory, and every
+// (row, block) pair that is expected to hold at least tau edges gets a SEGMENT of 16-bit block-local
+// source ids in that block's stream.  A persistent CTA loads a block into shared memory with 128-bit
+// loads, then its warps stream the segments (coalesced 64-bit loads, 4 ids per lane), gather from
+// shared memory, and reduce lanes that belong to the same row with a segmented warp scan; one f32
+// partial per (row, block) pair goes back to HBM.  Edges of pairs below the threshold (and all edges
+// of short rows) stay in a SELL-32 layout with 32-bit ids: one lane per row, gathers through L1/L2
+// with the first 32 K sources mirrored in shared memory.  A finish kernel adds each row's partials
+// in a fixed order (f64), applies the update of page_rank.rs:148-158 and reduces the sweep error.
+// Everything is deterministic: bit-identical run to run and for every shard count.
+//
+// Multi-GPU (1-D edge-cut by destination): the 32-row slices of the internal order are dealt
+// round-robin to the P ranks, so every rank holds the same mix of hub and tail rows; a rank builds the
+// layout of its own rows only and stores each finished out_score into every peer's next vector
+// (multimem.st through the NVSwitch when a multicast mapping is given, else one store per peer).
 //
 // Algorithmic bytes per sweep: 4m (targets) + 4(n+1) (offsets) + 5*4n (out_scores read+write,
 // scores read+write, out-degree read) = 4m + 24n + 4  (BASELINE.md §3).
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <numeric>
 
 #include "common.cuh"
 
@@ -32,51 +45,83 @@ namespace gb {
 
 constexpr int PR_WARPS = 32;        // warps per CTA of the sweep kernels: one persistent CTA per SM
 constexpr int PR_THREADS = PR_WARPS * 32;
-constexpr int PR_HOT = 32 * 1024;   // out_scores entries mirrored in shared memory (128 KB; L1 keeps ~96 KB)
-constexpr int PR_HOT_MAX = 52 * 1024;  // upper bound of the GB_PR_HOT experiment knob
+constexpr int PR_HOT = 32 * 1024;   // out_scores entries mirrored in shared memory by the SELL kernel
+constexpr int PR_HOT_MAX = 52 * 1024;
 constexpr int PR_FIN_THREADS = 256;
-constexpr uint32_t PR_LONG_DEG = 256;  // rows with more in-edges are cut into segments, the rest go to SELL-32
-constexpr uint32_t PR_SEG = 256;       // edges per segment (8 per lane)
 constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;  // sweeps bracketed by CUDA events when profiling is on
+constexpr uint32_t CB_G = 4;                 // block-local ids per group (one 64-bit load per lane)
+constexpr uint32_t CB_BLOCK_DEFAULT = 32768; // source-vector entries per block (128 KB of shared memory)
+constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
+constexpr double CB_TAU_DEFAULT = 3.0;       // a (row, block) pair gets a segment if it expects >= tau edges
+constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
+constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
+// chunk flags (bits 24.. of PrChunk.w)
+constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
 
-// the share of a contiguous range of internal rows (the whole graph on one GPU, or one rank's shard
-// of the 1-D edge-cut) in the two layouts
-struct PrRange {
-  uint32_t row_begin = 0, row_end = 0;    // internal rows [row_begin, row_end), clipped to active rows
-  uint32_t long_begin = 0, long_end = 0;  // hub rows of the range
-  uint32_t seg_begin = 0, seg_end = 0;    // their segments
-  uint32_t slice_begin = 0, slice_end = 0;  // SELL slices of the range
-  uint32_t sell_row_end = 0;                // one past the last SELL row of the range
-  unsigned grid_seg = 0, grid_sell = 0, grid_fin = 1;
-  DevBuf<double> block_err;  // per CTA error partials (SELL CTAs, then finish CTAs)
-  DevBuf<double> err_hist;   // error of each sweep of the current batch
-  DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
-  uint64_t bytes() const { return block_err.bytes() + err_hist.bytes() + ctrl.bytes(); }
+// ---- the cyclic deal of 32-row slices over the ranks of the 1-D edge-cut ---------------------------
+struct PrDeal {
+  uint32_t P = 1, p = 0;
 };
+__host__ __device__ __forceinline__ uint32_t deal_global(uint32_t l, uint32_t P, uint32_t p) {
+  return (((l >> 5) * P + p) << 5) | (l & 31u);
+}
+// number of local rows whose global index is below R
+static inline uint32_t deal_count(uint32_t R, uint32_t P, uint32_t p) {
+  const uint32_t F = R >> 5, rem = R & 31u;
+  const uint32_t full = F > p ? (F - p + P - 1) / P : 0;
+  uint32_t c = full * 32;
+  if (rem && (F % P) == p) c += rem;
+  return c;
+}
 
 struct PrPlan {
   uint32_t n = 0;
-  uint32_t n_active = 0;  // rows with in-degree > 0 (renumbered to [0, n_active))
-  uint32_t n_long = 0;    // rows [0, n_long) have more than PR_LONG_DEG in-edges
+  uint32_t n_active = 0;  // global rows with in-degree > 0 (renumbered to [0, n_active))
   uint64_t m = 0;
-  uint32_t num_segs = 0, num_slices = 0;
+  PrDeal deal;
+  uint32_t n_loc = 0;     // local active rows
+  uint32_t n_cb = 0;      // local rows [0, n_cb) own at least one column-block segment
+  uint64_t loc_edges = 0; // in-edges of the local rows
+  uint64_t cb_edges = 0;  // of which served from column blocks
   DevBuf<uint32_t> new_id;    // old id -> internal id
-  DevBuf<uint32_t> off;       // internal in-CSR offsets [n+1] (plan-time and partitioning only)
   DevBuf<uint32_t> outdeg;    // out-degree by internal id [n]
-  DevBuf<uint32_t> seg_first; // first segment of each hub row [n_long+1]
-  DevBuf<uint4> seg_tgt;      // hub rows' targets, 64 uint4 per segment, tail padded with ~0
-  DevBuf<float> partial;      // one partial sum per segment
-  DevBuf<uint4> sell;         // SELL-32 targets: slice-major, then 4-edge group, then lane
+  // column blocks
+  uint32_t B = 0, KB = 0;       // block entries, hot blocks
+  uint64_t S = 0;               // staircase size = sum of nrows[j]
+  uint64_t NG = 0;              // groups in all block streams
+  uint32_t chunk_groups = 0, n_chunks = 0, n_tasks = 0, n_fix = 0;
+  DevBuf<uint32_t> blk;         // [KB] source block of hot rank j
+  DevBuf<uint32_t> nrows;       // [KB] local rows [0, nrows[j]) have a segment in block j (non-increasing)
+  DevBuf<uint32_t> poff;        // [KB+1] staircase offsets
+  DevBuf<uint2> cb_ids;         // [NG] groups of 4 block-local 16-bit ids (pad id = B)
+  DevBuf<uint32_t> cb_bits;     // [NG/32 + 4] bit g set <=> group g starts a segment
+  DevBuf<float> partial;        // [S] one partial sum per (block, row) pair
+  DevBuf<uint4> chunks;         // [n_chunks] (g_begin, g_end, row_before, j | flags << 24)
+  DevBuf<uint32_t> tail_slot;   // [n_chunks] staircase slot of the segment cut by the chunk end
+  DevBuf<double> side;          // [2 n_chunks] head / tail parts of segments cut by chunk boundaries
+  DevBuf<uint32_t> fix_list;    // [n_fix] chunks whose tail segment continues in later chunks
+  DevBuf<uint2> tasks;          // [n_tasks] chunk ranges of one block each
+  DevBuf<uint32_t> task_ctr;    // dynamic task counter
+  DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
+  // SELL-32 (all local active rows; rows < n_cb hold only the edges outside their segments)
+  uint32_t num_slices = 0;
+  DevBuf<uint4> sell;         // slice-major, then 4-edge group, then lane
   DevBuf<uint2> slice_meta;   // per slice: (first uint4 index, uint4 groups per lane)
-  DevBuf<float> x[2];         // out_scores ping-pong [n]
-  DevBuf<float> scores;       // ranks by internal id [n]
-  PrRange all;                // the whole active range (single-GPU path)
-  uint32_t hot_count = 0;     // entries of out_scores mirrored in shared memory by the sweep kernels
-  size_t smem_bytes = 0;      // dynamic shared memory of the sweep kernels
+  // state (single-GPU path; the shard API brings its own vectors)
+  DevBuf<float> x[2];
+  DevBuf<float> scores;
+  unsigned grid_cb = 0, grid_sell = 0, grid_fin = 1;
+  DevBuf<double> block_err;  // per CTA error partials (SELL CTAs, then finish CTAs)
+  DevBuf<double> err_hist;   // error of each sweep of the current batch
+  DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
+  uint32_t hot_count = 0;    // entries of out_scores mirrored in shared memory by the SELL kernel
+  size_t smem_sell = 0, smem_cb = 0;
   std::vector<cudaEvent_t> prof_events;
   uint64_t bytes() const {
-    return new_id.bytes() + off.bytes() + outdeg.bytes() + seg_first.bytes() + seg_tgt.bytes() + partial.bytes() +
-           sell.bytes() + slice_meta.bytes() + x[0].bytes() + x[1].bytes() + scores.bytes() + all.bytes();
+    return new_id.bytes() + outdeg.bytes() + blk.bytes() + nrows.bytes() + poff.bytes() + cb_ids.bytes() +
+           cb_bits.bytes() + partial.bytes() + chunks.bytes() + tail_slot.bytes() + side.bytes() +
+           fix_list.bytes() + tasks.bytes() + rem.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
+           x[1].bytes() + scores.bytes() + block_err.bytes() + err_hist.bytes();
   }
 };
 
@@ -95,9 +140,9 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint32_t* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -110,6 +155,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
   return v;
 }
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
 
 // ---- plan construction kernels ---------------------------------------------------------------
 __global__ void k_perm_keys(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ out_off,
@@ -117,9 +167,9 @@ __global__ void k_perm_keys(const uint32_t* __restrict__ in_off, const uint32_t*
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     uint32_t indeg = in_off[v + 1] - in_off[v];
     uint32_t outdeg = out_off[v + 1] - out_off[v];
-    // in-degree descending (rows of similar length become neighbours: SELL slices need no padding and
-    // hub rows come first), then out-degree descending (hot sources first inside equal in-degrees).
-    // R-MAT's expected in- and out-degree of a vertex coincide, so this is also a hot-first order.
+    // in-degree descending (hub rows first, rows of similar length become neighbours), then
+    // out-degree descending (hot sources first inside equal in-degrees).  R-MAT's expected in- and
+    // out-degree of a vertex coincide, so this is also a hot-first order of the SOURCES.
     keys[v] = ((uint64_t)(uint32_t)(~indeg) << 32) | (uint32_t)(~outdeg);
     ids[v] = v;
   }
@@ -138,27 +188,297 @@ __global__ void k_perm_scatter(const uint32_t* __restrict__ sorted_ids, const ui
     indeg[r] = in_off[v + 1] - in_off[v];
   }
 }
+__global__ void k_count_active(const uint32_t* __restrict__ indeg, uint32_t n, uint32_t* __restrict__ count) {
+  uint32_t act = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) act += indeg[r] > 0;
+  for (int o = 16; o > 0; o >>= 1) act += __shfl_xor_sync(0xFFFFFFFFu, act, o);
+  if ((threadIdx.x & 31) == 0 && act) atomicAdd(count, act);
+}
+// out-edges leaving each source block (one CTA per block): the block's share of all gathers
+__global__ void k_blk_edges(const uint32_t* __restrict__ outdeg, uint32_t n, uint32_t B,
+                            unsigned long long* __restrict__ blk_edges) {
+  __shared__ unsigned long long part[8];
+  const uint32_t b = blockIdx.x;
+  const uint64_t lo = (uint64_t)b * B, hi = min((uint64_t)n, lo + B);
+  unsigned long long s = 0;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += outdeg[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += part[w];
+    blk_edges[b] = t;
+  }
+}
+// rows_ge[b] = number of (global) rows with in-degree >= dmin[b]; indeg is non-increasing
+__global__ void k_rows_ge(const uint32_t* __restrict__ indeg, uint32_t n_active, const uint32_t* __restrict__ dmin,
+                          uint32_t nblk, uint32_t* __restrict__ rows_ge) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x) {
+    const uint32_t d = dmin[b];
+    uint32_t lo = 0, hi = n_active;  // first index with indeg < d
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (indeg[mid] >= d) lo = mid + 1;
+      else hi = mid;
+    }
+    rows_ge[b] = lo;
+  }
+}
+
+// One warp per local row that owns segments: classify its in-edges.  An edge from source s (internal
+// id) lands in block s / B; if that block is hot (rank j) and the row is inside the block's row prefix
+// it belongs to segment (j, row), else to the row's SELL remainder.  The same traversal order is
+// used by the fill kernel, so positions inside a segment follow the CSR order: deterministic.
+__global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                           const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
+                           const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
+                           const uint32_t* __restrict__ poff, uint32_t B, uint32_t n_cb, PrDeal deal,
+                           uint32_t* __restrict__ cnt, uint32_t* __restrict__ lens,
+                           unsigned long long* __restrict__ cb_edges) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long in_cb = 0;
+  for (uint32_t l = warp; l < n_cb; l += nwarps) {
+    const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
+    const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
+    uint32_t rem = 0;
+    for (uint32_t i = 0; i < d; i += 32) {
+      const bool valid = i + lane < d;
+      uint32_t j = CB_NONE;
+      if (valid) {
+        const uint32_t s = new_id[in_tgt[b0 + i + lane]];
+        j = hot_of_blk[s / B];
+        if (j != CB_NONE && l >= nrows[j]) j = CB_NONE;
+      }
+      const bool cb = j != CB_NONE;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j);
+      if (cb && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(cnt + poff[j] + l, (uint32_t)__popc(peers));
+      rem += __popc(__ballot_sync(0xFFFFFFFFu, valid && !cb));
+    }
+    if (lane == 0) {
+      lens[l] = rem;
+      in_cb += d - rem;
+    }
+  }
+  if (lane == 0 && in_cb) atomicAdd(cb_edges, in_cb);
+}
+__global__ void k_lens_tail(const uint32_t* __restrict__ indeg, uint32_t n_cb, uint32_t n_loc, PrDeal deal,
+                            uint32_t* __restrict__ lens) {
+  for (uint32_t l = n_cb + blockIdx.x * blockDim.x + threadIdx.x; l < n_loc; l += gridDim.x * blockDim.x)
+    lens[l] = indeg[deal_global(l, deal.P, deal.p)];
+}
+__global__ void k_loc_edges(const uint32_t* __restrict__ indeg, uint32_t n_loc, PrDeal deal,
+                            unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < n_loc; l += gridDim.x * blockDim.x)
+    s += indeg[deal_global(l, deal.P, deal.p)];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+// edges of a pair -> groups of its segment (every pair of the staircase keeps at least one group, so
+// that the row of a group follows from counting segment starts)
+__global__ void k_cb_groups(uint32_t* __restrict__ cnt, uint64_t S) {
+  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < S; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = cnt[e];
+    cnt[e] = c ? (c + CB_G - 1) / CB_G : 1u;
+  }
+}
+__global__ void k_fill_u2(uint2* __restrict__ a, uint64_t count, uint2 v) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    a[i] = v;
+}
+__global__ void k_cb_bits(const uint32_t* __restrict__ goff, uint64_t S, uint32_t* __restrict__ bits) {
+  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < S; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t g = goff[e];
+    atomicOr(bits + (g >> 5), 1u << (g & 31u));
+  }
+}
+// SELL slice widths: the longest lane of the slice, in 4-edge groups
+__global__ void k_sell_widths(const uint32_t* __restrict__ lens, uint32_t n_loc, uint32_t num_slices,
+                              uint32_t* __restrict__ units) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t sidx = warp; sidx < num_slices; sidx += nwarps) {
+    const uint32_t l = 32 * sidx + lane;
+    const uint32_t w = warp_max(l < n_loc ? lens[l] : 0u);
+    if (lane == 0) units[sidx] = ((w + 3) / 4) * 32;  // uint4 entries of the slice
+  }
+}
+__global__ void k_sell_meta(const uint32_t* __restrict__ units, const uint32_t* __restrict__ bases,
+                            uint32_t num_slices, uint2* __restrict__ meta) {
+  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x)
+    meta[sidx] = make_uint2(bases[sidx], units[sidx] / 32);
+}
+// second traversal of the rows that own segments: block-local ids into the segments (CSR order inside
+// a segment), all other sources into the row's SELL lane
+__global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                          const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
+                          const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
+                          const uint32_t* __restrict__ poff, const uint32_t* __restrict__ blk, uint32_t B,
+                          uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff, uint32_t* __restrict__ cur,
+                          uint16_t* __restrict__ ids, const uint2* __restrict__ slice_meta,
+                          uint32_t* __restrict__ sell) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t l = warp; l < n_cb; l += nwarps) {
+    const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
+    const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
+    const uint2 meta = slice_meta[l >> 5];
+    uint32_t rem = 0;
+    for (uint32_t i = 0; i < d; i += 32) {
+      const bool valid = i + lane < d;
+      uint32_t j = CB_NONE, s = 0;
+      if (valid) {
+        s = new_id[in_tgt[b0 + i + lane]];
+        j = hot_of_blk[s / B];
+        if (j != CB_NONE && l >= nrows[j]) j = CB_NONE;
+      }
+      const bool cb = j != CB_NONE;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j);
+      uint32_t e = 0, base = 0;
+      if (cb) {
+        e = poff[j] + l;
+        base = cur[e];
+      }
+      __syncwarp();
+      if (cb) {
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        ids[(uint64_t)goff[e] * CB_G + base + rank] = (uint16_t)(s - blk[j] * B);
+        if (rank == 0) cur[e] = base + __popc(peers);
+      }
+      __syncwarp();
+      const uint32_t rb = __ballot_sync(0xFFFFFFFFu, valid && !cb);
+      if (valid && !cb) {
+        const uint32_t q = rem + __popc(rb & ((1u << lane) - 1u));
+        sell[((uint64_t)meta.x + (uint64_t)(q / 4) * 32 + (l & 31u)) * 4 + (q % 4)] = s;
+      }
+      rem += __popc(rb);
+    }
+  }
+}
+// rows without segments: the whole row goes to its SELL lane (one lane per row)
+__global__ void k_sell_fill_tail(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                                 const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
+                                 uint32_t n_cb, uint32_t n_loc, PrDeal deal, uint32_t num_slices,
+                                 const uint2* __restrict__ meta, uint4* __restrict__ sell) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t sidx = n_cb / 32 + warp; sidx < num_slices; sidx += nwarps) {
+    const uint2 m = meta[sidx];
+    const uint32_t l = 32 * sidx + lane;
+    if (l < n_cb) continue;  // filled by k_cb_fill (lanes of the boundary slice)
+    uint32_t b = 0, d = 0;
+    if (l < n_loc) {
+      const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
+      b = in_off[old];
+      d = in_off[old + 1] - b;
+    }
+    for (uint32_t q = 0; q * 4 < d; ++q) {
+      uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+      const uint32_t j = 4 * q;
+      if (j + 0 < d) v.x = new_id[in_tgt[b + j + 0]];
+      if (j + 1 < d) v.y = new_id[in_tgt[b + j + 1]];
+      if (j + 2 < d) v.z = new_id[in_tgt[b + j + 2]];
+      if (j + 3 < d) v.w = new_id[in_tgt[b + j + 3]];
+      sell[m.x + q * 32 + lane] = v;
+    }
+  }
+}
+__global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t count,
+                             uint32_t* __restrict__ dst) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+// Chunks: block j's stream [gbeg[j], gbeg[j+1]) is cut every C groups; a cut inside a segment moves to
+// the segment's end unless the segment is longer than C groups, in which case the cut stays and both
+// neighbours handle a PART of it (side buffer + fixup), so no warp ever owns more than 2C groups.
+struct CbCut {
+  uint32_t pos, row;
+  bool mid;
+};
+__device__ __forceinline__ CbCut cb_cut(const uint32_t* __restrict__ goff_j, uint32_t nr, uint32_t gend, uint32_t q,
+                                        uint32_t C) {
+  if (q >= gend) return CbCut{gend, nr, false};
+  uint32_t lo = 0, hi = nr;  // largest row with goff_j[row] <= q
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (goff_j[mid] <= q) lo = mid;
+    else hi = mid;
+  }
+  const uint32_t s0 = goff_j[lo], s1 = (lo + 1 < nr) ? goff_j[lo + 1] : gend;
+  if (s0 == q) return CbCut{q, lo, false};
+  if (s1 - s0 > C) return CbCut{q, lo, true};
+  return CbCut{s1, lo + 1, false};
+}
+__global__ void k_cb_chunks(const uint32_t* __restrict__ goff, const uint32_t* __restrict__ poff,
+                            const uint32_t* __restrict__ nrows, const uint32_t* __restrict__ gbeg,
+                            const uint32_t* __restrict__ cfirst, uint32_t KB, uint32_t n_chunks, uint32_t C,
+                            uint4* __restrict__ chunks, uint32_t* __restrict__ tail_slot,
+                            uint32_t* __restrict__ fix_list, uint32_t* __restrict__ n_fix) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = KB;  // block with cfirst[j] <= c < cfirst[j + 1]
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (cfirst[mid] <= c) lo = mid;
+      else hi = mid;
+    }
+    const uint32_t j = lo, k = c - cfirst[j];
+    const uint32_t* goff_j = goff + poff[j];
+    const uint32_t nr = nrows[j], g0 = gbeg[j], g1 = gbeg[j + 1];
+    const bool last = c + 1 == cfirst[j + 1];
+    const CbCut a = cb_cut(goff_j, nr, g1, g0 + k * C, C);
+    const CbCut b = last ? CbCut{g1, nr, false} : cb_cut(goff_j, nr, g1, g0 + (k + 1) * C, C);
+    uint32_t fl = 0;
+    if (a.mid) fl |= CB_HEAD_CONT;
+    if (b.mid) fl |= CB_TAIL_CONT;
+    const uint32_t last_row = b.mid ? b.row : b.row - 1;  // row of the chunk's last group
+    if (a.mid && last_row == a.row) fl |= CB_INTERIOR;
+    const uint32_t row_before = a.mid ? a.row : a.row - 1;
+    chunks[c] = make_uint4(a.pos, b.pos, row_before, j | (fl << 24));
+    tail_slot[c] = b.mid ? poff[j] + b.row : CB_NONE;
+    if (b.mid && !(fl & CB_INTERIOR)) fix_list[atomicAdd(n_fix, 1u)] = c;
+  }
+}
+
 // ---- sweep kernels (JACOBI) ------------------------------------------------------------------
 struct PrArgs {
   const uint32_t* outdeg;
   const float* x_cur;
   float* x_next;
+  float* mc_next;       // multicast mapping of x_next on every rank (NULL: unicast peer stores)
   float* peer_next[7];  // peer-mapped copies of x_next (fused allgather over NVLink); n_peers used
   uint32_t n_peers;
-  uint32_t hot_count;   // entries of x_cur mirrored in shared memory (multiple of 4)
+  uint32_t n;
+  uint32_t hot_count;   // entries of x_cur mirrored in shared memory by the SELL kernel (multiple of 4)
   float* scores;
-  // hub rows
-  const uint4* seg_tgt;
-  const uint32_t* seg_first;
+  PrDeal deal;
+  uint32_t n_loc, n_cb;
+  // column blocks
+  uint32_t B, KB;
+  const uint32_t* blk;
+  const uint32_t* nrows;
+  const uint32_t* poff;
+  const uint2* cb_ids;
+  const uint32_t* cb_bits;
   float* partial;
-  uint32_t seg_begin, seg_end;
-  uint32_t long_begin, long_end;
+  const uint4* chunks;
+  const uint32_t* tail_slot;
+  double* side;
+  const uint32_t* fix_list;
+  uint32_t n_fix;
+  const uint2* tasks;
+  uint32_t n_tasks;
+  uint32_t* task_ctr;
+  float* rem;
   // SELL rows
   const uint4* sell;
   const uint2* slice_meta;
-  uint32_t slice_begin, slice_end;
-  uint32_t sell_row0;     // row of lane 0 of slice 0 (= n_long)
-  uint32_t sell_row_end;  // one past the last SELL row of this range
+  uint32_t num_slices;
   // error / stop rule
   double* block_err;
   double* err_hist;
@@ -210,119 +530,190 @@ __device__ __forceinline__ float pr_sum8(const float (&v)[8]) {
 }
 __device__ __forceinline__ uint4 pr_ld4(const uint4* p) { return ld_stream_u4(reinterpret_cast<const uint32_t*>(p)); }
 
-// the per-vertex update of page_rank.rs:148-158 with the reference's rounding sequence
+// the per-vertex update of page_rank.rs:148-158 with the reference's rounding sequence; gr = global row
 template <bool PEERS>
-__device__ __forceinline__ double pr_update(uint32_t r, float sum, float old, uint32_t deg, const PrArgs& a) {
+__device__ __forceinline__ double pr_update(uint32_t gr, float sum, float old, uint32_t deg, const PrArgs& a) {
   const float nw = __fadd_rn(a.base, __fmul_rn(a.damping, sum));
-  a.scores[r] = nw;
+  a.scores[gr] = nw;
   const float xo = __fdiv_rn(nw, (float)deg);
-  a.x_next[r] = xo;
-  // fused allgather: the finished out_score also goes straight into every peer's next vector
-  if (PEERS)
-    for (uint32_t p = 0; p < a.n_peers; ++p) a.peer_next[p][r] = xo;
+  if (PEERS && a.mc_next) {
+    // one store, replicated by the NVSwitch into every rank's next vector (this rank's included)
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.mc_next + gr), "f"(xo) : "memory");
+  } else {
+    a.x_next[gr] = xo;
+    if (PEERS)
+      for (uint32_t p = 0; p < a.n_peers; ++p) a.peer_next[p][gr] = xo;
+  }
   return fabs((double)__fsub_rn(nw, old));
 }
 
-__device__ __forceinline__ void pr_load_hot(float* hot, const float* __restrict__ x, uint32_t hot_n) {
-  for (uint32_t i = threadIdx.x * 4; i < hot_n; i += PR_THREADS * 4)
-    *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
-  __syncthreads();
-}
-
-// ---- hub rows: 256-edge segments, 32 segments per slice, one lane per segment ----------------------
-// Divergent 4-byte gathers sustain ~0.95 per clock per SM on B200 whatever the load path
-// (profiles/r01_gather_ceiling_microbench.txt), so everything around the gathers is kept minimal.  A
-// slice interleaves 32 segments group-major / lane-minor exactly like a SELL slice of width 64: every
-// lane streams its own segment with 128-bit coalesced loads and keeps a private sum — there is no
-// cross-lane reduction (the shuffle tree of a warp-per-segment version cost a third of its time).
-__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_seg(const PrArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* hot = smem;
-  if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* x = a.x_cur;
-  const uint32_t hot_n = a.hot_count;
-  pr_load_hot(hot, x, hot_n);
-  const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
-  const uint32_t stride = gridDim.x * PR_WARPS;
-  const uint32_t slice_end = (a.seg_end + 31) / 32;
-  constexpr uint32_t W4 = PR_SEG / 4;  // uint4 groups per segment
-  for (uint32_t sl = a.seg_begin / 32 + blockIdx.x * PR_WARPS + warp; sl < slice_end; sl += stride) {
-    const uint4* base = a.seg_tgt + (size_t)sl * (W4 * 32) + lane;
-    uint4 ta = pr_ld4(base), tb = pr_ld4(base + 32);
-    float acc = 0.0f;
-#pragma unroll 2
-    for (uint32_t q = 0; q < W4; q += 2) {
-      const uint4 na = (q + 2 < W4) ? pr_ld4(base + (q + 2) * 32) : ta;
-      const uint4 nb = (q + 3 < W4) ? pr_ld4(base + (q + 3) * 32) : tb;
-      float v[8];
-      pr_gather(x, hot_saddr, hot_n, ta, tb, v);
-      acc += pr_sum8(v);
-      ta = na;
-      tb = nb;
+// ---- column blocks ------------------------------------------------------------------------------------
+// One warp, one chunk: groups [g0, g1) of block j's stream, 32 groups (128 ids) per step.  Lanes of a
+// step that belong to the same row are combined by a segmented inclusive scan; a segment that spans
+// steps is carried in f64.  The row of a lane follows from counting segment-start bits.
+__device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint32_t c, uint32_t lane, uint32_t pad2) {
+  const uint4 ch = a.chunks[c];
+  const uint32_t g0 = ch.x, g1 = ch.y;
+  if (g0 >= g1) return;
+  uint32_t row_before = ch.z;
+  const uint32_t j = ch.w & 0xFFFFFFu, fl = ch.w >> 24;
+  const bool head_cont = fl & CB_HEAD_CONT, tail_cont = fl & CB_TAIL_CONT;
+  float* __restrict__ partial = a.partial + a.poff[j];
+  bool in_head = head_cont;
+  double carry = 0.0;
+  uint2 ids = make_uint2(pad2, pad2);
+  if (g0 + lane < g1) ids = ld_stream_u2(a.cb_ids + g0 + lane);
+  const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+  for (uint32_t gs = g0; gs < g1; gs += 32) {
+    uint2 nids = make_uint2(pad2, pad2);
+    if (gs + 32 + lane < g1) nids = ld_stream_u2(a.cb_ids + gs + 32 + lane);
+    const uint32_t wi = gs >> 5, sh = gs & 31u;
+    const uint32_t w0 = __ldg(a.cb_bits + wi), w1 = __ldg(a.cb_bits + wi + 1);
+    uint32_t flags = __funnelshift_r(w0, w1, sh);
+    const uint32_t nvalid = min(32u, g1 - gs);
+    if (nvalid < 32) flags &= (1u << nvalid) - 1u;
+    const bool last_step = gs + 32 >= g1;
+    // does the run of the last valid lane go on after this step (inside the chunk / past its end)?
+    const bool run_continues = last_step ? tail_cont : !((w1 >> sh) & 1u);
+    float v = (xs[ids.x & 0xFFFFu] + xs[ids.x >> 16]) + (xs[ids.y & 0xFFFFu] + xs[ids.y >> 16]);
+    const uint32_t below = flags & le_mask;
+    const int seg_start = below ? 31 - __clz(below) : -1;
+    const int lo = seg_start < 0 ? 0 : seg_start;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+      if ((int)lane - d >= lo) v += t;
     }
-    const uint32_t seg = sl * 32 + lane;
-    if (seg >= a.seg_begin && seg < a.seg_end) a.partial[seg] = acc;
+    const uint32_t last = nvalid - 1;
+    const bool is_end = lane < nvalid && (lane == last || ((flags >> (lane + 1)) & 1u));
+    const double tot = (double)v + (seg_start < 0 ? carry : 0.0);
+    if (is_end && !(lane == last && run_continues && !last_step)) {
+      if (in_head && seg_start < 0) a.side[2 * (size_t)c] = tot;              // tail part of a cut segment
+      else if (lane == last && last_step && tail_cont) a.side[2 * (size_t)c + 1] = tot;  // head part of one
+      else partial[row_before + __popc(below)] = (float)tot;
+    }
+    const double tl = __shfl_sync(0xFFFFFFFFu, tot, last);
+    carry = (run_continues && !last_step) ? tl : 0.0;
+    if (flags) in_head = false;
+    row_before += __popc(flags);
+    ids = nids;
   }
 }
 
-// ---- SELL-32 sweep for rows with at most PR_LONG_DEG in-edges -------------------------------------
-// Rows are sorted by in-degree, so the 32 rows of a slice have (almost) the same length: one lane per
-// row, no reduction, no per-row offsets.  A lane reads its row four targets at a time (128-bit,
-// coalesced: the slice is stored group-major, lane-minor), gathers, and adds in row order.  The next
-// slice's first targets and row metadata are requested while the current slice is processed.
+__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
+  __shared__ uint32_t s_task;
+  if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t B = a.B;
+  const uint32_t pad2 = B | (B << 16);
+  uint32_t cur_j = CB_NONE;
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(a.task_ctr, 1u);
+    __syncthreads();
+    const uint32_t t = s_task;
+    __syncthreads();
+    if (t >= a.n_tasks) break;
+    const uint2 task = a.tasks[t];
+    const uint32_t j = a.chunks[task.x].w & 0xFFFFFFu;
+    if (j != cur_j) {
+      const uint64_t x0 = (uint64_t)a.blk[j] * B;
+      const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
+      for (uint32_t i = threadIdx.x * 4; i < B; i += PR_THREADS * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x0 + i + 3 < a.n) {
+          v = __ldg(src + i / 4);
+        } else {
+          if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
+          if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
+          if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
+        }
+        *reinterpret_cast<float4*>(xs + i) = v;
+      }
+      if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
+      cur_j = j;
+      __syncthreads();
+    }
+    for (uint32_t c = task.x + warp; c < task.y; c += PR_WARPS) cb_chunk(a, xs, c, lane, pad2);
+  }
+}
+
+// ---- SELL-32 sweep: one lane per row ------------------------------------------------------------
+// A lane reads its row four targets at a time (128-bit, coalesced: the slice is stored group-major,
+// lane-minor), gathers, and adds in row order.  The next slice's first targets and row metadata are
+// requested while the current slice is processed.  Rows below n_cb only hold the edges that are not in
+// a column-block segment: their sum goes to rem[] and the finish kernel completes them.
+// Prologue: segments cut by chunk boundaries get their parts added in a fixed order (the column-block
+// kernel ran before this one on the stream).
 template <bool PEERS>
 __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* hot = smem;
   __shared__ double warp_err[PR_WARPS];
   if (a.ctrl[0] != 0) return;
+  for (uint32_t i = blockIdx.x * PR_THREADS + threadIdx.x; i < a.n_fix; i += gridDim.x * PR_THREADS) {
+    const uint32_t c0 = a.fix_list[i];
+    double t = a.side[2 * (size_t)c0 + 1];
+    uint32_t k = c0 + 1;
+    for (;; ++k) {
+      const uint32_t fl = a.chunks[k].w >> 24;
+      t += a.side[2 * (size_t)k];
+      if (!((fl & CB_INTERIOR) && (fl & CB_TAIL_CONT))) break;
+    }
+    a.partial[a.tail_slot[c0]] = (float)t;
+  }
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ x = a.x_cur;
   const uint32_t hot_n = a.hot_count;
-  pr_load_hot(hot, x, hot_n);
+  for (uint32_t i = threadIdx.x * 4; i < hot_n; i += PR_THREADS * 4)
+    *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
+  __syncthreads();
   const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
   double err = 0.0;
   const uint32_t stride = gridDim.x * PR_WARPS;
   const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
-  uint32_t sidx = a.slice_begin + blockIdx.x * PR_WARPS + warp;
+  const uint32_t P = a.deal.P, pp = a.deal.p;
+  uint32_t sidx = blockIdx.x * PR_WARPS + warp;
   // pipeline state: metadata of this and the next slice, first two target groups + row data of this one
   uint2 meta = make_uint2(0, 0), nmeta = meta;
   uint4 ta = pad, tb = pad;
   float old = 0.0f;
   uint32_t deg = 1;
-  if (sidx < a.slice_end) {
+  if (sidx < a.num_slices) {
     meta = __ldg(a.slice_meta + sidx);
-    if (sidx + stride < a.slice_end) nmeta = __ldg(a.slice_meta + sidx + stride);
+    if (sidx + stride < a.num_slices) nmeta = __ldg(a.slice_meta + sidx + stride);
     const uint4* base = a.sell + meta.x + lane;
     if (0 < meta.y) ta = pr_ld4(base);
     if (1 < meta.y) tb = pr_ld4(base + 32);
-    const uint32_t row = a.sell_row0 + 32 * sidx + lane;
-    if (row < a.sell_row_end) {
-      old = a.scores[row];
-      deg = a.outdeg[row];
+    const uint32_t l = 32 * sidx + lane;
+    if (l >= a.n_cb && l < a.n_loc) {
+      const uint32_t gr = deal_global(l, P, pp);
+      old = a.scores[gr];
+      deg = a.outdeg[gr];
     }
   }
-  while (sidx < a.slice_end) {
+  while (sidx < a.num_slices) {
     const uint32_t w4 = meta.y;
     const uint4* base = a.sell + meta.x + lane;
-    const uint32_t row = a.sell_row0 + 32 * sidx + lane;
+    const uint32_t l = 32 * sidx + lane;
     // next slice: first groups, row data; metadata of the slice after it
     const uint32_t nidx = sidx + stride;
     uint4 nta = pad, ntb = pad;
     float nold = 0.0f;
     uint32_t ndeg = 1;
     uint2 nnmeta = make_uint2(0, 0);
-    if (nidx < a.slice_end) {
+    if (nidx < a.num_slices) {
       const uint4* nbase = a.sell + nmeta.x + lane;
       if (0 < nmeta.y) nta = pr_ld4(nbase);
       if (1 < nmeta.y) ntb = pr_ld4(nbase + 32);
-      const uint32_t nrow = a.sell_row0 + 32 * nidx + lane;
-      if (nrow < a.sell_row_end) {
-        nold = a.scores[nrow];
-        ndeg = a.outdeg[nrow];
+      const uint32_t nl = 32 * nidx + lane;
+      if (nl >= a.n_cb && nl < a.n_loc) {
+        const uint32_t ngr = deal_global(nl, P, pp);
+        nold = a.scores[ngr];
+        ndeg = a.outdeg[ngr];
       }
-      if (nidx + stride < a.slice_end) nnmeta = __ldg(a.slice_meta + nidx + stride);
+      if (nidx + stride < a.num_slices) nnmeta = __ldg(a.slice_meta + nidx + stride);
     }
     float acc = 0.0f;
     for (uint32_t q = 0; q < w4; q += 2) {
@@ -335,7 +726,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
       ta = na;
       tb = nb;
     }
-    if (row < a.sell_row_end) err += pr_update<PEERS>(row, acc, old, deg, a);
+    if (l < a.n_cb) a.rem[l] = acc;
+    else if (l < a.n_loc) err += pr_update<PEERS>(deal_global(l, P, pp), acc, old, deg, a);
     sidx = nidx;
     meta = nmeta;
     nmeta = nnmeta;
@@ -355,8 +747,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
   }
 }
 
-// ---- finish: hub rows = sum of their segment partials (fixed order), then the sweep error ---------
-// One warp per hub row; the last CTA to finish reduces all CTA error partials in a fixed order and
+// ---- finish: rows with segments = partials of their blocks (fixed order, f64) + SELL remainder -----
+// One lane per row; the last CTA to finish reduces all CTA error partials in a fixed order and
 // evaluates the stop rule of page_rank.rs:107 on the device.
 template <bool PEERS>
 __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
@@ -365,20 +757,29 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   __shared__ bool is_last;
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
   double err = 0.0;
-  const uint32_t nwarps = gridDim.x * FIN_WARPS;
-  for (uint32_t r = a.long_begin + blockIdx.x * FIN_WARPS + warp; r < a.long_end; r += nwarps) {
-    const uint32_t sb = a.seg_first[r], se = a.seg_first[r + 1];
+  const uint32_t P = a.deal.P, pp = a.deal.p;
+  for (uint32_t l0 = (blockIdx.x * FIN_WARPS + warp) * 32; l0 < a.n_cb; l0 += gridDim.x * FIN_WARPS * 32) {
+    const uint32_t l = l0 + lane;
+    const bool on = l < a.n_cb;
     float old = 0.0f;
     uint32_t deg = 1;
-    if (lane == 0) {
-      old = a.scores[r];
-      deg = a.outdeg[r];
+    uint32_t gr = 0;
+    double s = 0.0;
+    if (on) {
+      gr = deal_global(l, P, pp);
+      old = a.scores[gr];
+      deg = a.outdeg[gr];
+      s = (double)a.rem[l];
     }
-    float p = 0.0f;
-    for (uint32_t j = sb + lane; j < se; j += 32) p += a.partial[j];
-    p = warp_sum(p);
-    if (lane == 0) err += pr_update<PEERS>(r, p, old, deg, a);
+    // nrows[] is non-increasing: the first block whose prefix ends at or before l0 ends the loop
+    for (uint32_t j = 0; j < a.KB; ++j) {
+      const uint32_t nr = __ldg(a.nrows + j);
+      if (nr <= l0) break;
+      if (l < nr) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
+    }
+    if (on) err += pr_update<PEERS>(gr, (float)s, old, deg, a);
   }
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
@@ -412,97 +813,19 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   }
 }
 
-// ---- plan-time helpers of the two layouts ---------------------------------------------------------
-__global__ void k_count_rows(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ counts) {
-  uint32_t act = 0, lng = 0;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    const uint32_t d = off[r + 1] - off[r];
-    act += d > 0;
-    lng += d > PR_LONG_DEG;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    act += __shfl_xor_sync(0xFFFFFFFFu, act, o);
-    lng += __shfl_xor_sync(0xFFFFFFFFu, lng, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (act) atomicAdd(counts + 0, act);
-    if (lng) atomicAdd(counts + 1, lng);
-  }
-}
-__global__ void k_seg_counts(const uint32_t* __restrict__ off, uint32_t n_long, uint32_t* __restrict__ cnt) {
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_long; r += gridDim.x * blockDim.x)
-    cnt[r] = (r < n_long) ? (off[r + 1] - off[r] + PR_SEG - 1) / PR_SEG : 0;
-}
-// one warp per hub row: copy its (renumbered) sources into its padded segments (slice-interleaved
-// layout: segment s lives in slice s/32 as lane s%32; element j of it is component j%4 of group j/4)
-__global__ void k_seg_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                           const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
-                           const uint32_t* __restrict__ seg_first, uint32_t n_long, uint32_t* __restrict__ out) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = warp; r < n_long; r += nwarps) {
-    const uint32_t old = old_of[r];
-    const uint32_t b = in_off[old], d = in_off[old + 1] - b;
-    const uint32_t s0 = seg_first[r];
-    for (uint32_t j = lane; j < d; j += 32) {
-      const uint32_t sg = s0 + j / PR_SEG, e = j % PR_SEG;
-      const uint64_t idx = (((uint64_t)(sg / 32) * (PR_SEG / 4) + e / 4) * 32 + (sg % 32)) * 4 + (e % 4);
-      out[idx] = new_id[in_tgt[b + j]];
-    }
-  }
-}
-__global__ void k_sell_widths(const uint32_t* __restrict__ off, uint32_t row0, uint32_t num_slices,
-                              uint32_t* __restrict__ units) {
-  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x) {
-    const uint32_t r = row0 + 32 * sidx;  // rows are sorted by degree: the first row of a slice is its longest
-    units[sidx] = ((off[r + 1] - off[r] + 3) / 4) * 32;  // uint4 entries of the slice
-  }
-}
-__global__ void k_sell_meta(const uint32_t* __restrict__ units, const uint32_t* __restrict__ bases,
-                            uint32_t num_slices, uint2* __restrict__ meta) {
-  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x)
-    meta[sidx] = make_uint2(bases[sidx], units[sidx] / 32);
-}
-__global__ void k_sell_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                            const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
-                            uint32_t row0, uint32_t row_end, uint32_t num_slices, const uint2* __restrict__ meta,
-                            uint4* __restrict__ sell) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t sidx = warp; sidx < num_slices; sidx += nwarps) {
-    const uint2 m = meta[sidx];
-    const uint32_t row = row0 + 32 * sidx + lane;
-    uint32_t b = 0, d = 0;
-    if (row < row_end) {
-      const uint32_t old = old_of[row];
-      b = in_off[old];
-      d = in_off[old + 1] - b;
-    }
-    for (uint32_t q = 0; q < m.y; ++q) {
-      uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
-      const uint32_t j = 4 * q;
-      if (j + 0 < d) v.x = new_id[in_tgt[b + j + 0]];
-      if (j + 1 < d) v.y = new_id[in_tgt[b + j + 1]];
-      if (j + 2 < d) v.z = new_id[in_tgt[b + j + 2]];
-      if (j + 3 < d) v.w = new_id[in_tgt[b + j + 3]];
-      sell[m.x + q * 32 + lane] = v;
-    }
-  }
-}
-
-__global__ void k_pr_init(uint32_t n, uint32_t n_active, float init, float base,
+// own == 0: scores of rows this rank does not own stay 0 so that the ranks' vectors can be summed
+__global__ void k_pr_init(uint32_t n, uint32_t n_active, float init, float base, PrDeal deal,
                           const uint32_t* __restrict__ outdeg, float* __restrict__ x0,
                           float* __restrict__ x1, float* __restrict__ scores) {
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     float d = (float)outdeg[r];
     x0[r] = __fdiv_rn(init, d);  // page_rank.rs:75-79; +inf for dangling vertices, never gathered
+    const bool mine = ((r >> 5) % deal.P) == deal.p;
     if (r < n_active) {
-      scores[r] = init;
+      scores[r] = mine ? init : 0.0f;
     } else {
       // no in-edges: after the first sweep score == base + damping * 0 == base, for ever
-      scores[r] = base;
+      scores[r] = deal.p == 0 ? base : 0.0f;
       x1[r] = __fdiv_rn(base, d);
     }
   }
@@ -568,66 +891,53 @@ __global__ void __launch_bounds__(32) k_pr_exact(const uint32_t* __restrict__ in
   }
 }
 
-// ---- chunking of a row range -------------------------------------------------------------------
-static gb_status build_range(const gb_graph* g, const PrPlan* p, uint32_t row_begin, uint32_t row_end,
-                             PrRange* r) {
-  cudaStream_t s = g->stream;
-  if (row_end > p->n_active) row_end = p->n_active;  // rows without in-edges are never swept
-  if (row_begin > row_end) row_begin = row_end;
-  r->row_begin = row_begin;
-  r->row_end = row_end;
-  // SELL part: rows [max(row_begin, n_long), row_end) — shard boundaries sit on slice boundaries
-  const uint32_t sb = std::max(row_begin, p->n_long), se = std::max(row_end, p->n_long);
-  r->slice_begin = r->slice_end = 0;
-  r->sell_row_end = se;
-  if (sb < se) {  // an empty SELL share (e.g. a range that starts at n_active) needs no alignment
-    GB_REQUIRE((sb - p->n_long) % 32 == 0, "shard boundary %u is not on a SELL slice boundary", row_begin);
-    r->slice_begin = (sb - p->n_long) / 32;
-    r->slice_end = (se - p->n_long + 31) / 32;
-  }
-  // hub rows of the range and their segments
-  r->long_begin = std::min(row_begin, p->n_long);
-  r->long_end = std::min(row_end, p->n_long);
-  r->seg_begin = r->seg_end = 0;
-  if (p->n_long) {
-    uint32_t h[2] = {0, 0};
-    GB_CUDA(cudaMemcpyAsync(&h[0], p->seg_first.p + r->long_begin, 4, cudaMemcpyDeviceToHost, s));
-    GB_CUDA(cudaMemcpyAsync(&h[1], p->seg_first.p + r->long_end, 4, cudaMemcpyDeviceToHost, s));
-    GB_CUDA(cudaStreamSynchronize(s));
-    r->seg_begin = h[0];
-    r->seg_end = h[1];
-  }
-  int dev_sms = 148;
-  GB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
-  const uint64_t seg_slices = r->seg_end > r->seg_begin ? (r->seg_end + 31) / 32 - r->seg_begin / 32 : 0;
-  const uint64_t want_seg = (seg_slices + PR_WARPS - 1) / PR_WARPS;
-  r->grid_seg = (unsigned)std::min<uint64_t>(want_seg, (uint64_t)dev_sms);  // one persistent CTA per SM
-  const uint64_t want_sell = ((uint64_t)(r->slice_end - r->slice_begin) + PR_WARPS - 1) / PR_WARPS;
-  r->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms);
-  const uint64_t want_fin = ((uint64_t)(r->long_end - r->long_begin) + (PR_FIN_THREADS / 32) - 1) / (PR_FIN_THREADS / 32);
-  r->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
-  const size_t nerr = (size_t)r->grid_sell + r->grid_fin;
-  GB_TRY(r->block_err.alloc(nerr));
-  GB_CUDA(cudaMemsetAsync(r->block_err.p, 0, nerr * sizeof(double), s));
-  GB_TRY(r->err_hist.alloc(64));
-  GB_TRY(r->ctrl.alloc(2));
-  GB_CUDA(cudaMemsetAsync(r->ctrl.p, 0, 8, s));
+// ---- plan ------------------------------------------------------------------------------------
+template <typename T>
+static gb_status scan_exclusive(cudaStream_t s, T* data, uint64_t count) {
+  GB_REQUIRE(count < (1ull << 31), "scan of %llu items is too long", (unsigned long long)count);
+  size_t tb = 0;
+  GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, data, data, (int)count, s));
+  DevBuf<uint8_t> tmp;
+  GB_TRY(tmp.alloc(tb));
+  GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, data, data, (int)count, s));
   GB_CUDA(cudaStreamSynchronize(s));
   return GB_OK;
 }
+template <typename T>
+static gb_status upload(cudaStream_t s, DevBuf<T>* dst, const std::vector<T>& src, size_t pad = 0) {
+  GB_TRY(dst->alloc(std::max<size_t>(src.size(), 1), pad));
+  if (!src.empty()) GB_CUDA(cudaMemcpyAsync(dst->p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaStreamSynchronize(s));  // src may be a temporary
+  return GB_OK;
+}
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* e = getenv(name);
+  return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : dflt;
+}
 
-// ---- plan ------------------------------------------------------------------------------------
-static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
+static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan) {
   cudaStream_t s = g->stream;
   const uint32_t n = g->n;
   const uint64_t m = g->in.len;
+  GB_REQUIRE(deal.P >= 1 && deal.p < deal.P, "bad shard %u of %u", deal.p, deal.P);
   PrPlan* p = new (std::nothrow) PrPlan();
   if (!p) return fail(GB_ERR_OOM, "host allocation failed");
   p->n = n;
   p->m = m;
+  p->deal = deal;
   gb_status st = [&]() -> gb_status {
+    int dev_sms = 148;
+    GB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
+    // knobs (experiments; defaults are the measured optima)
+    uint32_t B = env_u32("GB_PR_BLOCK", CB_BLOCK_DEFAULT);
+    B = std::min<uint32_t>(std::max<uint32_t>(B & ~1023u, 1024u), CB_BLOCK_MAX);
+    double tau = CB_TAU_DEFAULT;
+    if (const char* e = getenv("GB_PR_TAU")) tau = atof(e);
+    if (!(tau > 0.0)) tau = 1e30;  // tau <= 0 switches the column blocks off
+    p->B = B;
     // 1. permutation: in-degree descending, then out-degree descending, then id
     DevBuf<uint32_t> old_of;  // internal id -> original id (plan-time only)
+    DevBuf<uint32_t> indeg;   // in-degree by internal id (plan-time only)
     {
       DevBuf<uint64_t> keys, keys_alt;
       DevBuf<uint32_t> ids, ids_alt;
@@ -645,50 +955,116 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kb, vb, (int)n, 0, 64, s));
       GB_TRY(p->new_id.alloc(n));
       GB_TRY(p->outdeg.alloc(n));
-      GB_TRY(p->off.alloc((size_t)n + 1));
+      GB_TRY(indeg.alloc((size_t)n + 1));
       k_perm_scatter<<<grid_for(n, 256), 256, 0, s>>>(vb.Current(), g->out.off.p, g->in.off.p, n, p->new_id.p,
-                                                     p->outdeg.p, p->off.p);
+                                                     p->outdeg.p, indeg.p);
       GB_TRY(old_of.alloc(n));
       GB_CUDA(cudaMemcpyAsync(old_of.p, vb.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
-    // 2. internal offsets = running sum of the permuted in-degrees.  The rows themselves are never
-    //    materialised in internal order: the two layouts below are filled straight from the original
-    //    in-CSR through old_of / new_id (a row keeps its original entry order, which fixes the
-    //    summation order; no billion-key sort on the build path).
+    // 2. active rows (a prefix of the internal order) and this rank's share of them
+    DevBuf<unsigned long long> counters;  // [0] active rows, [1] local edges, [2] edges in segments, [3] fix count
+    GB_TRY(counters.alloc(4));
+    GB_CUDA(cudaMemsetAsync(counters.p, 0, 32, s));
+    k_count_active<<<grid_for(n, 256), 256, 0, s>>>(indeg.p, n, reinterpret_cast<uint32_t*>(counters.p));
     {
-      size_t tb = 0;
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p->off.p, p->off.p, (int64_t)n + 1, s));
-      DevBuf<uint8_t> tmp;
-      GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p->off.p, p->off.p, (int64_t)n + 1, s));
+      unsigned long long h = 0;
+      GB_CUDA(cudaMemcpyAsync(&h, counters.p, 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
+      p->n_active = (uint32_t)h;
     }
-    // 3. row classes: rows are ordered by in-degree, so both classes are prefixes
+    p->n_loc = deal_count(p->n_active, deal.P, deal.p);
+    if (p->n_loc) k_loc_edges<<<grid_for(p->n_loc, 256), 256, 0, s>>>(indeg.p, p->n_loc, deal, counters.p + 1);
+    // 3. hot blocks: block b carries the share e_b / m of all gathers; a row of in-degree d expects
+    //    d * e_b / m edges from it, and gets a segment when that is at least tau
+    const uint32_t nblk = (uint32_t)(((uint64_t)n + B - 1) / B);
+    std::vector<uint32_t> h_hot(nblk, CB_NONE), h_blk, h_nrows, h_poff;
+    if (p->n_loc && m) {
+      DevBuf<unsigned long long> blk_edges;
+      DevBuf<uint32_t> dmin, rows_ge;
+      GB_TRY(blk_edges.alloc(nblk));
+      GB_TRY(dmin.alloc(nblk));
+      GB_TRY(rows_ge.alloc(nblk));
+      k_blk_edges<<<nblk, 256, 0, s>>>(p->outdeg.p, n, B, blk_edges.p);
+      std::vector<unsigned long long> h_edges(nblk);
+      GB_CUDA(cudaMemcpyAsync(h_edges.data(), blk_edges.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      std::vector<uint32_t> h_dmin(nblk, 0xFFFFFFFFu);
+      for (uint32_t b = 0; b < nblk; ++b)
+        if (h_edges[b]) {
+          const double d = std::ceil(tau * (double)m / (double)h_edges[b]);
+          h_dmin[b] = d >= 4294967295.0 ? 0xFFFFFFFFu : std::max<uint32_t>(1u, (uint32_t)d);
+        }
+      GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)nblk * 4, cudaMemcpyHostToDevice, s));
+      k_rows_ge<<<grid_for(nblk, 128), 128, 0, s>>>(indeg.p, p->n_active, dmin.p, nblk, rows_ge.p);
+      std::vector<uint32_t> h_rows(nblk);
+      GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      std::vector<uint32_t> order;
+      for (uint32_t b = 0; b < nblk; ++b)
+        if (h_dmin[b] != 0xFFFFFFFFu && deal_count(h_rows[b], deal.P, deal.p) > 0) order.push_back(b);
+      std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return h_rows[x] != h_rows[y] ? h_rows[x] > h_rows[y] : x < y;
+      });
+      if (order.size() > CB_MAX_BLOCKS) order.resize(CB_MAX_BLOCKS);
+      uint64_t S = 0;
+      for (uint32_t j = 0; j < order.size(); ++j) {
+        const uint32_t b = order[j];
+        h_hot[b] = j;
+        h_blk.push_back(b);
+        h_nrows.push_back(deal_count(h_rows[b], deal.P, deal.p));
+        h_poff.push_back((uint32_t)S);
+        S += h_nrows.back();
+        GB_REQUIRE(S < 0xFFFFFFF0ull, "column-block staircase too large (%llu pairs)", (unsigned long long)S);
+      }
+      h_poff.push_back((uint32_t)S);
+      p->S = S;
+    }
+    p->KB = (uint32_t)h_blk.size();
+    p->n_cb = p->KB ? h_nrows[0] : 0;
+    if (h_poff.empty()) h_poff.push_back(0);
+    DevBuf<uint32_t> hot_of_blk;
+    GB_TRY(upload(s, &hot_of_blk, h_hot));
+    GB_TRY(upload(s, &p->blk, h_blk));
+    GB_TRY(upload(s, &p->nrows, h_nrows));
+    GB_TRY(upload(s, &p->poff, h_poff));
+    // 4. segment sizes (pairs of the staircase) and SELL lane lengths
+    DevBuf<uint32_t> goff;  // [S + 1] edges per pair -> groups per pair -> first group of each pair
+    DevBuf<uint32_t> lens;  // [n_loc] SELL lane lengths
+    GB_TRY(goff.alloc(p->S + 1));
+    GB_CUDA(cudaMemsetAsync(goff.p, 0, (p->S + 1) * 4, s));
+    GB_TRY(lens.alloc(std::max<uint32_t>(p->n_loc, 1)));
+    if (p->n_cb)
+      k_cb_count<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, p->n_cb, deal,
+          goff.p, lens.p, counters.p + 2);
+    if (p->n_loc > p->n_cb)
+      k_lens_tail<<<grid_for(p->n_loc - p->n_cb, 256), 256, 0, s>>>(indeg.p, p->n_cb, p->n_loc, deal, lens.p);
+    if (p->S) {
+      k_cb_groups<<<grid_for(p->S, 256), 256, 0, s>>>(goff.p, p->S);
+      GB_TRY(scan_exclusive(s, goff.p, p->S + 1));
+      uint32_t ng = 0;
+      GB_CUDA(cudaMemcpyAsync(&ng, goff.p + p->S, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      p->NG = ng;
+    }
     {
-      DevBuf<uint32_t> counts;
-      GB_TRY(counts.alloc(2));
-      GB_CUDA(cudaMemsetAsync(counts.p, 0, 8, s));
-      k_count_rows<<<grid_for(n, 256), 256, 0, s>>>(p->off.p, n, counts.p);
-      uint32_t h[2] = {0, 0};
-      GB_CUDA(cudaMemcpyAsync(h, counts.p, 8, cudaMemcpyDeviceToHost, s));
+      unsigned long long h[3] = {0, 0, 0};
+      GB_CUDA(cudaMemcpyAsync(h, counters.p, 24, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      p->n_active = h[0];
-      p->n_long = h[1];
+      p->loc_edges = h[1];
+      p->cb_edges = h[2];
     }
-    // 3b. SELL-32 layout of rows [n_long, n_active)
-    p->num_slices = (p->n_active - p->n_long + 31) / 32;
+    // 5. SELL-32 layout of all local rows
+    p->num_slices = (p->n_loc + 31) / 32;
     if (p->num_slices) {
       DevBuf<uint32_t> units, bases;
       GB_TRY(units.alloc(p->num_slices));
       GB_TRY(bases.alloc(p->num_slices));
-      k_sell_widths<<<grid_for(p->num_slices, 256), 256, 0, s>>>(p->off.p, p->n_long, p->num_slices, units.p);
-      size_t tb = 0;
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, units.p, bases.p, (int)p->num_slices, s));
-      DevBuf<uint8_t> tmp;
-      GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units.p, bases.p, (int)p->num_slices, s));
+      k_sell_widths<<<grid_for((uint64_t)p->num_slices * 32, 256), 256, 0, s>>>(lens.p, p->n_loc, p->num_slices, units.p);
+      GB_CUDA(cudaMemcpyAsync(bases.p, units.p, (size_t)p->num_slices * 4, cudaMemcpyDeviceToDevice, s));
+      GB_TRY(scan_exclusive(s, bases.p, p->num_slices));
       uint32_t last_base = 0, last_units = 0;
       GB_CUDA(cudaMemcpyAsync(&last_base, bases.p + p->num_slices - 1, 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaMemcpyAsync(&last_units, units.p + p->num_slices - 1, 4, cudaMemcpyDeviceToHost, s));
@@ -696,49 +1072,109 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
       const size_t total_units = (size_t)last_base + last_units;
       GB_TRY(p->slice_meta.alloc(p->num_slices));
       GB_TRY(p->sell.alloc(total_units, 64));
+      GB_CUDA(cudaMemsetAsync(p->sell.p, 0xFF, (total_units + 64) * sizeof(uint4), s));  // ~0 = padding
       k_sell_meta<<<grid_for(p->num_slices, 256), 256, 0, s>>>(units.p, bases.p, p->num_slices, p->slice_meta.p);
-      k_sell_fill<<<grid_for((uint64_t)p->num_slices * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, p->n_long, p->n_active, p->num_slices,
-          p->slice_meta.p, p->sell.p);
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
-    // 3c. hub rows: padded 256-edge segments
-    p->num_segs = 0;
-    GB_TRY(p->seg_first.alloc((size_t)p->n_long + 1));
-    {
-      k_seg_counts<<<grid_for((uint64_t)p->n_long + 1, 256), 256, 0, s>>>(p->off.p, p->n_long, p->seg_first.p);
-      size_t tb = 0;
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p->seg_first.p, p->seg_first.p, (int)(p->n_long + 1), s));
-      DevBuf<uint8_t> tmp;
-      GB_TRY(tmp.alloc(tb));
-      GB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p->seg_first.p, p->seg_first.p, (int)(p->n_long + 1), s));
-      GB_CUDA(cudaMemcpyAsync(&p->num_segs, p->seg_first.p + p->n_long, 4, cudaMemcpyDeviceToHost, s));
+    // 6. fill: segments + SELL remainders of the rows below n_cb, whole rows above
+    GB_TRY(p->cb_ids.alloc(std::max<uint64_t>(p->NG, 1), 64));
+    GB_TRY(p->cb_bits.alloc(p->NG / 32 + 4));
+    GB_CUDA(cudaMemsetAsync(p->cb_bits.p, 0, (p->NG / 32 + 4) * 4, s));
+    if (p->NG) {
+      k_fill_u2<<<grid_for(p->NG + 64, 256), 256, 0, s>>>(p->cb_ids.p, p->NG + 64, make_uint2(B | (B << 16), B | (B << 16)));
+      k_cb_bits<<<grid_for(p->S, 256), 256, 0, s>>>(goff.p, p->S, p->cb_bits.p);
+      DevBuf<uint32_t> cur;
+      GB_TRY(cur.alloc(p->S));
+      GB_CUDA(cudaMemsetAsync(cur.p, 0, p->S * 4, s));
+      k_cb_fill<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, p->n_cb,
+          deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
+          reinterpret_cast<uint32_t*>(p->sell.p));
+      GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
-    const size_t seg_slices = ((size_t)p->num_segs + 31) / 32;
-    GB_TRY(p->seg_tgt.alloc(seg_slices * 32 * (PR_SEG / 4), 64));
-    GB_CUDA(cudaMemsetAsync(p->seg_tgt.p, 0xFF, (seg_slices * 32 * (PR_SEG / 4) + 64) * sizeof(uint4), s));  // ~0 = padding
-    GB_TRY(p->partial.alloc(std::max<size_t>(p->num_segs, 1)));
-    if (p->num_segs) {
-      k_seg_fill<<<grid_for((uint64_t)p->n_long * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, p->seg_first.p, p->n_long,
-          reinterpret_cast<uint32_t*>(p->seg_tgt.p));
+    if (p->n_loc > p->n_cb) {
+      k_sell_fill_tail<<<grid_for((uint64_t)(p->num_slices - p->n_cb / 32) * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, p->n_cb, p->n_loc, deal, p->num_slices, p->slice_meta.p,
+          p->sell.p);
       GB_CUDA(cudaGetLastError());
     }
-    GB_CUDA(cudaStreamSynchronize(s));
+    // 7. chunks and tasks of the column-block kernel
+    if (p->NG) {
+      // first group of every block's stream
+      DevBuf<uint32_t> gbeg;
+      GB_TRY(gbeg.alloc(p->KB + 1));
+      k_gather_u32<<<grid_for(p->KB + 1, 128), 128, 0, s>>>(goff.p, p->poff.p, p->KB + 1, gbeg.p);
+      std::vector<uint32_t> h_gbeg(p->KB + 1);
+      GB_CUDA(cudaMemcpyAsync(h_gbeg.data(), gbeg.p, (size_t)(p->KB + 1) * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      // a task (one block load) should be ~1/8 of an SM's share; 64+ chunks per task keep 32 warps busy
+      uint64_t task_groups = std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 8), 2048);
+      uint32_t C = env_u32("GB_PR_CHUNK", 0);
+      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(((task_groups / 64) + 31) / 32 * 32, 64), 1024);
+      C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
+      const uint32_t TC = (uint32_t)std::max<uint64_t>(32, (task_groups + C - 1) / C);
+      p->chunk_groups = C;
+      std::vector<uint32_t> h_cfirst(p->KB + 1, 0);
+      std::vector<uint2> h_tasks;
+      for (uint32_t j = 0; j < p->KB; ++j) {
+        const uint32_t G = h_gbeg[j + 1] - h_gbeg[j];
+        const uint32_t nc = (G + C - 1) / C;
+        h_cfirst[j + 1] = h_cfirst[j] + nc;
+        for (uint32_t c = 0; c < nc; c += TC)
+          h_tasks.push_back(make_uint2(h_cfirst[j] + c, h_cfirst[j] + std::min(nc, c + TC)));
+      }
+      p->n_chunks = h_cfirst[p->KB];
+      p->n_tasks = (uint32_t)h_tasks.size();
+      DevBuf<uint32_t> cfirst;
+      GB_TRY(upload(s, &cfirst, h_cfirst));
+      GB_TRY(upload(s, &p->tasks, h_tasks));
+      GB_TRY(p->chunks.alloc(p->n_chunks, 1));
+      GB_TRY(p->tail_slot.alloc(p->n_chunks));
+      GB_TRY(p->fix_list.alloc(p->n_chunks));
+      GB_TRY(p->side.alloc((size_t)2 * p->n_chunks + 2));
+      GB_CUDA(cudaMemsetAsync(p->side.p, 0, ((size_t)2 * p->n_chunks + 2) * 8, s));
+      GB_CUDA(cudaMemsetAsync(p->chunks.p + p->n_chunks, 0, sizeof(uint4), s));  // sentinel: ends every fixup walk
+      uint32_t* d_nfix = reinterpret_cast<uint32_t*>(counters.p + 3);
+      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, cfirst.p, p->KB,
+                                                           p->n_chunks, C, p->chunks.p, p->tail_slot.p,
+                                                           p->fix_list.p, d_nfix);
+      GB_CUDA(cudaGetLastError());
+      GB_CUDA(cudaMemcpyAsync(&p->n_fix, d_nfix, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+    } else {
+      GB_TRY(p->chunks.alloc(1));
+      GB_TRY(p->tail_slot.alloc(1));
+      GB_TRY(p->fix_list.alloc(1));
+      GB_TRY(p->side.alloc(2));
+      GB_TRY(p->tasks.alloc(1));
+    }
+    GB_TRY(p->partial.alloc(std::max<uint64_t>(p->S, 1)));
+    GB_CUDA(cudaMemsetAsync(p->partial.p, 0, std::max<uint64_t>(p->S, 1) * 4, s));
+    GB_TRY(p->rem.alloc(std::max<uint32_t>(p->n_cb, 1)));
+    GB_TRY(p->task_ctr.alloc(1));
+    GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
+    // 8. launch shapes and error buffers
     uint32_t hot_cap = PR_HOT;
     if (const char* e = getenv("GB_PR_HOT")) hot_cap = std::min<uint32_t>((uint32_t)PR_HOT_MAX, (uint32_t)atoi(e)) & ~3u;
     p->hot_count = std::min<uint32_t>(hot_cap, n & ~3u);
-    p->smem_bytes = (size_t)p->hot_count * sizeof(float) + 16;
-    GB_CUDA(cudaFuncSetAttribute(k_pr_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    // 4. chunking of the whole active range + state vectors
-    GB_TRY(build_range(g, p, 0, p->n_active, &p->all));
-    GB_TRY(p->x[0].alloc(n));
-    GB_TRY(p->x[1].alloc(n));
-    GB_TRY(p->scores.alloc(n));
+    p->smem_sell = (size_t)p->hot_count * sizeof(float) + 16;
+    p->smem_cb = ((size_t)B + 4) * sizeof(float);
+    GB_CUDA(cudaFuncSetAttribute(k_pr_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sell));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sell));
+    p->grid_cb = (unsigned)std::min<uint64_t>(p->n_tasks, (uint64_t)dev_sms);  // one persistent CTA per SM
+    const uint64_t want_sell = ((uint64_t)p->num_slices + PR_WARPS - 1) / PR_WARPS;
+    p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms);
+    const uint64_t want_fin = ((uint64_t)p->n_cb + PR_FIN_THREADS - 1) / PR_FIN_THREADS;
+    p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
+    const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
+    GB_TRY(p->block_err.alloc(nerr));
+    GB_CUDA(cudaMemsetAsync(p->block_err.p, 0, nerr * sizeof(double), s));
+    GB_TRY(p->err_hist.alloc(64));
+    GB_TRY(p->ctrl.alloc(2));
+    GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
     GB_CUDA(cudaStreamSynchronize(s));
     return GB_OK;
   }();
@@ -750,32 +1186,60 @@ static gb_status build_pr_plan(const gb_graph* g, PrPlan** out_plan) {
   return GB_OK;
 }
 
-static PrArgs make_args(const PrPlan* p, const PrRange* rg, float base, float damping, double tolerance) {
+static PrArgs make_args(const PrPlan* p, float base, float damping, double tolerance) {
   PrArgs a{};
   a.outdeg = p->outdeg.p;
-  a.seg_tgt = p->seg_tgt.p;
-  a.seg_first = p->seg_first.p;
+  a.n = p->n;
+  a.deal = p->deal;
+  a.n_loc = p->n_loc;
+  a.n_cb = p->n_cb;
+  a.B = p->B;
+  a.KB = p->KB;
+  a.blk = p->blk.p;
+  a.nrows = p->nrows.p;
+  a.poff = p->poff.p;
+  a.cb_ids = p->cb_ids.p;
+  a.cb_bits = p->cb_bits.p;
   a.partial = p->partial.p;
-  a.seg_begin = rg->seg_begin;
-  a.seg_end = rg->seg_end;
-  a.long_begin = rg->long_begin;
-  a.long_end = rg->long_end;
+  a.chunks = p->chunks.p;
+  a.tail_slot = p->tail_slot.p;
+  a.side = p->side.p;
+  a.fix_list = p->fix_list.p;
+  a.n_fix = p->n_fix;
+  a.tasks = p->tasks.p;
+  a.n_tasks = p->n_tasks;
+  a.task_ctr = p->task_ctr.p;
+  a.rem = p->rem.p;
   a.sell = p->sell.p;
   a.slice_meta = p->slice_meta.p;
-  a.slice_begin = rg->slice_begin;
-  a.slice_end = rg->slice_end;
-  a.sell_row0 = p->n_long;
-  a.sell_row_end = rg->sell_row_end;
-  a.block_err = rg->block_err.p;
-  a.err_hist = rg->err_hist.p;
-  a.ctrl = rg->ctrl.p;
-  a.err_base_fin = rg->grid_sell;
+  a.num_slices = p->num_slices;
+  a.block_err = p->block_err.p;
+  a.err_hist = p->err_hist.p;
+  a.ctrl = p->ctrl.p;
+  a.err_base_fin = p->grid_sell;
   a.base = base;
   a.damping = damping;
   a.tolerance = tolerance;
   a.n_peers = 0;
+  a.mc_next = nullptr;
   a.hot_count = p->hot_count;
   return a;
+}
+
+// one sweep = column blocks, SELL rows (+ fixup of cut segments), finish; returns the launches made
+template <bool PEERS>
+static unsigned launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s) {
+  unsigned launches = 1;
+  if (p->grid_cb) {
+    k_pr_cb<<<p->grid_cb, PR_THREADS, p->smem_cb, s>>>(a);
+    ++launches;
+  }
+  if (p->grid_sell) {
+    k_pr_sell<PEERS><<<p->grid_sell, PR_THREADS, p->smem_sell, s>>>(a);
+    ++launches;
+  }
+  k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+  return launches;
 }
 
 // ---- drivers ---------------------------------------------------------------------------------
@@ -800,7 +1264,7 @@ static gb_status run_exact(const gb_graph* g, const gb_page_rank_config* cfg, fl
 
 static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, float* d_scores,
                             uint64_t* ran, double* error) {
-  if (!g->pr_plan) GB_TRY(build_pr_plan(g, &g->pr_plan));
+  if (!g->pr_plan) GB_TRY(build_pr_plan(g, PrDeal{}, &g->pr_plan));
   PrPlan* p = g->pr_plan;
   cudaStream_t s = g->stream;
   const uint32_t n = p->n;
@@ -808,14 +1272,19 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
   const float init = 1.0f / nf;                             // page_rank.rs:70
   const float base = (1.0f - cfg->damping_factor) / nf;     // page_rank.rs:71
   const bool profile = profiling_on();
+  if (!p->x[0].p) {
+    GB_TRY(p->x[0].alloc(n));
+    GB_TRY(p->x[1].alloc(n));
+    GB_TRY(p->scores.alloc(n));
+  }
 
-  k_pr_init<<<grid_for(n, 256), 256, 0, s>>>(n, p->n_active, init, base, p->outdeg.p, p->x[0].p, p->x[1].p,
+  k_pr_init<<<grid_for(n, 256), 256, 0, s>>>(n, p->n_active, init, base, p->deal, p->outdeg.p, p->x[0].p, p->x[1].p,
                                             p->scores.p);
-  PrRange* rg = &p->all;
-  GB_CUDA(cudaMemsetAsync(rg->ctrl.p, 0, 8, s));
+  GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   g->timing.kernel_launches += 1;
 
-  PrArgs a = make_args(p, rg, base, cfg->damping_factor, cfg->tolerance);
+  PrArgs a = make_args(p, base, cfg->damping_factor, cfg->tolerance);
   a.scores = p->scores.p;
 
   // max_iterations == 0 never satisfies `iteration == max_iterations` (page_rank.rs:107): the
@@ -850,11 +1319,8 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
         ev_used += 2;
         GB_CUDA(cudaEventRecord(e0, s));
       }
-      if (rg->grid_seg) k_pr_seg<<<rg->grid_seg, PR_THREADS, p->smem_bytes, s>>>(a);
-      if (rg->grid_sell) k_pr_sell<false><<<rg->grid_sell, PR_THREADS, p->smem_bytes, s>>>(a);
+      g->timing.kernel_launches += launch_sweep<false>(p, a, s);
       if (e1) GB_CUDA(cudaEventRecord(e1, s));
-      k_pr_finish<false><<<rg->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
-      g->timing.kernel_launches += 1 + (rg->grid_seg ? 1 : 0) + (rg->grid_sell ? 1 : 0);
       if (sweep_no == 1 && p->n_active < n) {
         // sources without in-edges change exactly once (init/deg -> base/deg): patch the buffer
         // sweep 1 has just finished reading
@@ -867,12 +1333,12 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
     done += batch;
     if (can_stop_early || done >= limit) {
       uint32_t ctrl0 = 0;
-      GB_CUDA(cudaMemcpyAsync(&ctrl0, rg->ctrl.p, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(&ctrl0, p->ctrl.p, 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
       if (ctrl0 != 0) stopped = ctrl0;
       const uint64_t last = stopped ? stopped : done;
       const uint32_t slot = (uint32_t)(last - (done - batch) - 1);
-      GB_CUDA(cudaMemcpyAsync(&last_err, rg->err_hist.p + slot, 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(&last_err, p->err_hist.p + slot, 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
     }
   }
@@ -913,7 +1379,7 @@ static gb_status page_rank_impl(const gb_graph* g, const gb_page_rank_config* cf
     GB_TRY(tmp_scores.alloc(g->n));
     d_scores = tmp_scores.p;
   }
-  if (mode == GB_PR_JACOBI && !g->pr_plan) GB_TRY(build_pr_plan(g, &g->pr_plan));  // not timed
+  if (mode == GB_PR_JACOBI && !g->pr_plan) GB_TRY(build_pr_plan(g, PrDeal{}, &g->pr_plan));  // not timed
   g->timing = gb_timing{};
   GB_CUDA(cudaEventRecord(g->ev_begin, s));
   if (mode == GB_PR_EXACT) GB_TRY(run_exact(g, cfg, d_scores, ran, error));
@@ -927,95 +1393,29 @@ static gb_status page_rank_impl(const gb_graph* g, const gb_page_rank_config* cf
   return GB_OK;
 }
 
-
-// ---- multi-GPU shard (1-D edge-cut by destination range) ----------------------------------------
 }  // namespace gb
 
+// ---- multi-GPU shard (1-D edge-cut by destination, 32-row slices dealt round-robin) ----------------
 struct gb_pr_shard {
   const gb_graph* graph = nullptr;
-  gb::PrRange range;
+  gb::PrPlan* plan = nullptr;
 };
-
-namespace gb {
-
-static gb_status shard_partition(const gb_graph* g, uint32_t parts, uint64_t row_cost, const double* cuts,
-                                 uint32_t* ranges) {
-  // greedy_node_map_partition (graph_ops.rs:479-509) over the INTERNAL row order with
-  // node_map = in-degree and batch = ceil(m / parts) (in_degree_partition, graph_ops.rs:431-439)
-  if (!g->pr_plan) GB_TRY(build_pr_plan(g, &g->pr_plan));
-  const PrPlan* p = g->pr_plan;
-  std::vector<uint32_t> off((size_t)p->n + 1);
-  GB_CUDA(cudaMemcpyAsync(off.data(), p->off.p, off.size() * 4, cudaMemcpyDeviceToHost, g->stream));
-  GB_CUDA(cudaStreamSynchronize(g->stream));
-  // node_map = in-degree + a constant per-row charge: a row costs its gathers plus ~5 vector accesses,
-  // a division and (multi-GPU) one store per peer, so ranks owning millions of 1-edge rows would
-  // otherwise be the stragglers.  GB_SHARD_ROW_COST overrides the charge (0 = the plain rule).
-  if (const char* e = getenv("GB_SHARD_ROW_COST")) row_cost = (uint64_t)atoll(e);
-  const uint64_t total = p->m + row_cost * p->n_active;
-  const uint64_t batch = (total + parts - 1) / parts;
-  uint32_t count = 0;
-  uint64_t acc = 0;
-  ranges[0] = 0;
-  if (cuts) {
-    // explicit cut points (fractions of the total weight, increasing): used by the measured-time
-    // rebalancing of the multi-GPU orchestration
-    for (uint32_t k = 0; k + 1 < parts; ++k)
-      GB_REQUIRE(cuts[k] > 0.0 && cuts[k] < 1.0 && (k == 0 || cuts[k] >= cuts[k - 1]), "bad cut fraction %u", k);
-    for (uint32_t v = 0; v < p->n && count < parts - 1; ++v) {
-      const uint32_t d = off[v + 1] - off[v];
-      acc += d + (d ? row_cost : 0);
-      while (count < parts - 1 && (double)acc >= cuts[count] * (double)total) ranges[++count] = v + 1;
-    }
-    while (count < parts) ranges[++count] = p->n;
-  } else {
-    for (uint32_t v = 0; v < p->n; ++v) {
-      const uint32_t d = off[v + 1] - off[v];
-      acc += d + (d ? row_cost : 0);
-      if ((count < parts - 1 && acc >= batch) || v == p->n - 1) {
-        ranges[++count] = v + 1;
-        acc = 0;
-      }
-    }
-  }
-  for (uint32_t i = count + 1; i <= parts; ++i) ranges[i] = p->n;
-  // boundaries inside the SELL region move to the nearest slice boundary (32 rows)
-  for (uint32_t i = 1; i < parts; ++i) {
-    uint32_t b = ranges[i];
-    if (b > p->n_long && b < p->n_active) {
-      b = p->n_long + ((b - p->n_long + 16) / 32) * 32;
-      if (b > p->n_active) b = p->n_active;
-    }
-    if (b < ranges[i - 1]) b = ranges[i - 1];
-    ranges[i] = b;
-  }
-  return GB_OK;
-}
-
-}  // namespace gb
 
 extern "C" {
 
-gb_status gb_pr_shard_partition(const gb_graph* g, uint32_t parts, uint32_t row_cost, const double* cuts,
-                                uint32_t* ranges) {
-  GB_REQUIRE(g && ranges, "NULL argument");
-  GB_REQUIRE(parts >= 1, "parts must be >= 1");
-  if (g->kind != GB_KIND_DIRECTED) return gb::fail(GB_ERR_UNSUPPORTED, "page rank shards need a directed graph");
-  gb::DeviceGuard guard(g->device);
-  std::lock_guard<std::mutex> lock(g->mu);
-  return gb::shard_partition(g, parts, row_cost, cuts, ranges);
-}
-
-gb_status gb_pr_shard_create(const gb_graph* g, uint32_t row_begin, uint32_t row_end, gb_pr_shard** shard) {
+gb_status gb_pr_shard_create(const gb_graph* g, uint32_t rank, uint32_t world, gb_pr_shard** shard) {
   GB_REQUIRE(g && shard, "NULL argument");
   if (g->kind != GB_KIND_DIRECTED) return gb::fail(GB_ERR_UNSUPPORTED, "page rank shards need a directed graph");
-  GB_REQUIRE(row_begin <= row_end && row_end <= g->n, "bad row range [%u, %u)", row_begin, row_end);
+  GB_REQUIRE(world >= 1 && rank < world, "bad shard %u of %u", rank, world);
   gb::DeviceGuard guard(g->device);
   std::lock_guard<std::mutex> lock(g->mu);
-  if (!g->pr_plan) GB_TRY(gb::build_pr_plan(g, &g->pr_plan));
   gb_pr_shard* sh = new (std::nothrow) gb_pr_shard();
   if (!sh) return gb::fail(GB_ERR_OOM, "host allocation failed");
   sh->graph = g;
-  gb_status st = gb::build_range(g, g->pr_plan, row_begin, row_end, &sh->range);
+  gb::PrDeal deal;
+  deal.P = world;
+  deal.p = rank;
+  gb_status st = gb::build_pr_plan(g, deal, &sh->plan);
   if (st != GB_OK) {
     delete sh;
     return st;
@@ -1027,6 +1427,7 @@ gb_status gb_pr_shard_create(const gb_graph* g, uint32_t row_begin, uint32_t row
 gb_status gb_pr_shard_free(gb_pr_shard* shard) {
   if (!shard) return GB_OK;
   gb::DeviceGuard guard(shard->graph->device);
+  gb::free_pr_plan(shard->plan);
   delete shard;
   return GB_OK;
 }
@@ -1035,56 +1436,51 @@ gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0,
                            float* d_scores, void* cuda_stream) {
   GB_REQUIRE(shard && d_x0 && d_x1 && d_scores, "NULL argument");
   const gb_graph* g = shard->graph;
-  const gb::PrPlan* p = g->pr_plan;
+  const gb::PrPlan* p = shard->plan;
   gb::DeviceGuard guard(g->device);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const float nf = (float)p->n;
   const float init = 1.0f / nf;
   const float base = (1.0f - damping) / nf;
   // every rank fills the whole initial vector itself (no exchange needed before sweep 1)
-  gb::k_pr_init<<<gb::grid_for(p->n, 256), 256, 0, s>>>(p->n, p->n_active, init, base, p->outdeg.p, d_x0, d_x1,
-                                                       d_scores);
-  GB_CUDA(cudaMemsetAsync(shard->range.ctrl.p, 0, 8, s));
+  gb::k_pr_init<<<gb::grid_for(p->n, 256), 256, 0, s>>>(p->n, p->n_active, init, base, p->deal, p->outdeg.p, d_x0,
+                                                       d_x1, d_scores);
+  GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }
 
 gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t sweep_no, const float* d_x_cur,
                            float* d_x_next, float* const* d_peer_x_next, uint32_t peer_count,
-                           float* d_scores, double* d_error, void* cuda_stream) {
+                           float* d_mc_x_next, float* d_scores, double* d_error, void* cuda_stream) {
   GB_REQUIRE(shard && d_x_cur && d_x_next && d_scores && d_error, "NULL argument");
   GB_REQUIRE(peer_count <= 7, "at most 7 peers");
-  GB_REQUIRE(peer_count == 0 || d_peer_x_next, "peer pointer array is NULL");
+  GB_REQUIRE(peer_count == 0 || d_peer_x_next || d_mc_x_next, "peer pointer array is NULL");
   GB_REQUIRE(sweep_no >= 1, "sweep_no is 1-based");
   const gb_graph* g = shard->graph;
-  const gb::PrPlan* p = g->pr_plan;
-  const gb::PrRange* rg = &shard->range;
+  const gb::PrPlan* p = shard->plan;
   gb::DeviceGuard guard(g->device);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const float nf = (float)p->n;
   const float init = 1.0f / nf;
   const float base = (1.0f - damping) / nf;
-  gb::PrArgs a = gb::make_args(p, rg, base, damping, -1.0 /* the caller owns the stop rule */);
+  gb::PrArgs a = gb::make_args(p, base, damping, -1.0 /* the caller owns the stop rule */);
   a.x_cur = d_x_cur;
   a.x_next = d_x_next;
   a.scores = d_scores;
-  a.n_peers = peer_count;
-  for (uint32_t i = 0; i < peer_count; ++i) a.peer_next[i] = d_peer_x_next[i];
+  a.n_peers = d_mc_x_next ? 0 : peer_count;
+  a.mc_next = d_mc_x_next;
+  for (uint32_t i = 0; i < a.n_peers; ++i) a.peer_next[i] = d_peer_x_next[i];
   a.err_hist = d_error;
   a.sweep = 0;
   a.sweep_no = (uint32_t)std::min<uint64_t>(sweep_no, 0xFFFFFFFFull);
-  // the closed-form error of the rows without in-edges is contributed once, by the shard owning row 0
-  a.extra_err = (sweep_no == 1 && rg->row_begin == 0)
+  // the closed-form error of the rows without in-edges is contributed once, by rank 0
+  a.extra_err = (sweep_no == 1 && p->deal.p == 0)
                     ? (double)(p->n - p->n_active) * fabs((double)(base - init))
                     : 0.0;
-  if (rg->grid_seg) gb::k_pr_seg<<<rg->grid_seg, gb::PR_THREADS, p->smem_bytes, s>>>(a);
-  if (peer_count) {
-    if (rg->grid_sell) gb::k_pr_sell<true><<<rg->grid_sell, gb::PR_THREADS, p->smem_bytes, s>>>(a);
-    gb::k_pr_finish<true><<<rg->grid_fin, gb::PR_FIN_THREADS, 0, s>>>(a);
-  } else {
-    if (rg->grid_sell) gb::k_pr_sell<false><<<rg->grid_sell, gb::PR_THREADS, p->smem_bytes, s>>>(a);
-    gb::k_pr_finish<false><<<rg->grid_fin, gb::PR_FIN_THREADS, 0, s>>>(a);
-  }
+  if (peer_count || d_mc_x_next) gb::launch_sweep<true>(p, a, s);
+  else gb::launch_sweep<false>(p, a, s);
   if (sweep_no == 1 && p->n_active < p->n)
     gb::k_pr_fill_inactive<<<gb::grid_for(p->n - p->n_active, 256), 256, 0, s>>>(
         p->n, p->n_active, base, p->outdeg.p, const_cast<float*>(d_x_cur));
@@ -1096,7 +1492,7 @@ gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_int
                              void* cuda_stream) {
   GB_REQUIRE(shard && d_scores_internal && d_scores_out, "NULL argument");
   const gb_graph* g = shard->graph;
-  const gb::PrPlan* p = g->pr_plan;
+  const gb::PrPlan* p = shard->plan;
   gb::DeviceGuard guard(g->device);
   gb::k_unpermute<<<gb::grid_for(p->n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_scores_internal, p->new_id.p,
                                                                                  p->n, d_scores_out);
@@ -1104,30 +1500,48 @@ gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_int
   return GB_OK;
 }
 
-gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32_t* row_end,
-                           uint32_t* active_rows, uint64_t* edges) {
-  GB_REQUIRE(shard, "NULL argument");
-  const gb::PrRange* rg = &shard->range;
-  if (row_begin) *row_begin = rg->row_begin;
-  if (row_end) *row_end = rg->row_end;
-  if (active_rows) *active_rows = shard->graph->pr_plan->n_active;
-  if (edges) {
-    const gb::PrPlan* p = shard->graph->pr_plan;
-    uint32_t h[2] = {0, 0};
-    gb::DeviceGuard guard(shard->graph->device);
-    GB_CUDA(cudaMemcpy(&h[0], p->off.p + rg->row_begin, 4, cudaMemcpyDeviceToHost));
-    GB_CUDA(cudaMemcpy(&h[1], p->off.p + rg->row_end, 4, cudaMemcpyDeviceToHost));
-    *edges = (uint64_t)h[1] - h[0];
-  }
+gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
+  GB_REQUIRE(shard && stats, "NULL argument");
+  const gb::PrPlan* p = shard->plan;
+  stats->rank = p->deal.p;
+  stats->world = p->deal.P;
+  stats->active_rows = p->n_active;
+  stats->local_rows = p->n_loc;
+  stats->local_edges = p->loc_edges;
+  stats->block_edges = p->cb_edges;
+  stats->block_entries = p->B;
+  stats->hot_blocks = p->KB;
+  stats->segments = p->S;
+  stats->groups = p->NG;
+  stats->chunks = p->n_chunks;
+  stats->tasks = p->n_tasks;
+  stats->cut_segments = p->n_fix;
+  stats->chunk_groups = p->chunk_groups;
+  stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0);
+  stats->device_bytes = p->bytes();
   return GB_OK;
 }
 
-}  // extern "C"
+gb_status gb_page_rank_plan_info(const gb_graph* g, gb_pr_shard_stats* stats) {
+  GB_REQUIRE(g && stats, "NULL argument");
+  if (g->kind != GB_KIND_DIRECTED) return gb::fail(GB_ERR_UNSUPPORTED, "page rank needs a directed graph");
+  gb::DeviceGuard guard(g->device);
+  std::lock_guard<std::mutex> lock(g->mu);
+  if (!g->pr_plan) GB_TRY(gb::build_pr_plan(g, gb::PrDeal{}, &g->pr_plan));
+  gb_pr_shard tmp;
+  tmp.graph = g;
+  tmp.plan = g->pr_plan;
+  return gb_pr_shard_info(&tmp, stats);
+}
 
-namespace gb {
-}  // namespace gb
-
-extern "C" {
+gb_status gb_page_rank_plan_reset(const gb_graph* g) {
+  GB_REQUIRE(g, "NULL argument");
+  gb::DeviceGuard guard(g->device);
+  std::lock_guard<std::mutex> lock(g->mu);
+  gb::free_pr_plan(g->pr_plan);
+  g->pr_plan = nullptr;
+  return GB_OK;
+}
 
 gb_status gb_page_rank(const gb_graph* graph, const gb_page_rank_config* config, float* scores,
                        uint64_t* ran_iterations, double* error) {

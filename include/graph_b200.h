@@ -79,7 +79,12 @@ typedef enum gb_pr_mode {
   GB_PR_EXACT = 1,   /* the reference's sweep as ONE thread runs it: in place, CSR-order f32 sums
                         (page_rank.rs:142-160). Bit-exact with the reference whenever the reference
                         itself is deterministic (n <= CHUNK_SIZE = 16384, page_rank.rs:12). Sequential. */
-  GB_PR_JACOBI = 2   /* throughput path: double-buffered sweep (every read sees iteration k), deterministic */
+  GB_PR_JACOBI = 2   /* throughput path: double-buffered sweep (every read sees iteration k), deterministic.
+                        CAVEAT for drop-in callers: the reference sweep is in place (Gauss-Seidel-like,
+                        and schedule dependent for n > 16384), so with the reference's DEFAULT config
+                        (tolerance 1e-4) JACOBI meets the tolerance at a different sweep count and returns
+                        ranks ~1e-3 away from an in-place run; both converge to the same fixed point.  Use
+                        tolerance 0 + a fixed sweep count, or a tight tolerance, when comparing. */
 } gb_pr_mode;
 
 typedef struct gb_page_rank_config {
@@ -220,41 +225,59 @@ gb_status gb_sssp_device(const gb_graph* graph, const gb_sssp_config* config, fl
 /* global_triangle_count(&graph) -> u64                      triangle_count.rs:22-86 */
 gb_status gb_triangle_count(const gb_graph* graph, uint64_t* triangles);
 
-/* ---- multi-GPU PageRank shard (1-D edge-cut by destination range) ---------------------------
- * One process per GPU (torch.distributed / NCCL own the plumbing).  The JACOBI path renumbers
- * vertices internally (rows with in-edges first, then out-degree descending); shards are ranges of
- * INTERNAL rows, identical on every rank because every rank derives them from the same graph.
- * Rank p sweeps rows [ranges[p], ranges[p+1]) and owns that slice of the out_scores vector; the
- * slices are exchanged once per sweep, either by the caller (NCCL allgather) or by the sweep
- * kernel itself storing each finished value into the peers' next vectors (fused allgather). */
+/* ---- PageRank layout statistics / multi-GPU shard (1-D edge-cut by destination) -----------------
+ * The JACOBI path renumbers vertices internally (in-degree descending, then out-degree descending)
+ * and column-blocks the sweep (graph_b200/csrc/pagerank.cu).  For N GPUs (one process per GPU;
+ * torch.distributed / NCCL own the plumbing) the 32-row slices of that internal order are dealt
+ * round-robin: rank p owns slices p, p + P, p + 2P, ... — every rank holds the same mix of hub and
+ * tail rows, derives its rows from the degree arrays alone and builds the layout of its own rows
+ * only.  (The reference's own partitioner, in_degree_partition over the ORIGINAL ids,
+ * graph_ops.rs:431-439, is gb_in_degree_partition below; contiguous ranges of the degree-sorted
+ * order would give rank 0 all hubs and rank P-1 millions of one-edge rows.)  Rank p owns the
+ * out_scores entries of its rows; they are exchanged once per sweep, either by the caller (NCCL
+ * all-gather) or by the sweep kernels themselves storing each finished value into the peers' next
+ * vectors (fused all-gather: one multimem.st through the NVSwitch, or one store per peer). */
 typedef struct gb_pr_shard gb_pr_shard;
+
+typedef struct gb_pr_shard_stats {
+  uint32_t rank, world;
+  uint32_t active_rows;        /* rows with in-edges, whole graph */
+  uint32_t local_rows;         /* of which owned by this shard */
+  uint64_t local_edges;        /* in-edges of the local rows */
+  uint64_t block_edges;        /* of which gathered from shared-memory column blocks */
+  uint32_t block_entries;      /* source-vector entries per column block */
+  uint32_t hot_blocks;         /* column blocks that own segments */
+  uint64_t segments;           /* (row, block) pairs with a segment */
+  uint64_t groups;             /* 4-id groups in all block streams */
+  uint32_t chunks, tasks, cut_segments, chunk_groups;
+  uint32_t launches_per_sweep;
+  uint64_t device_bytes;       /* HBM held by this layout */
+} gb_pr_shard_stats;
 
 /* the reference's own partitioner on the ORIGINAL ids: in_degree_partition (graph_ops.rs:431-439,
  * :479-509); ranges has parts+1 entries */
 gb_status gb_in_degree_partition(const gb_graph* graph, uint32_t parts, uint32_t* ranges);
-/* same greedy rule applied to the internal row order with node_map = in-degree + row_cost for rows
- * that have in-edges: ranges[0..parts] (parts+1 entries).  row_cost = 0 is the reference's plain
- * in_degree_partition; a row also costs ~5 vector accesses and, on the fused path, one remote store
- * per peer — measured ~2 edge-equivalents without and ~18 with 7 peers (profiles/r01_multigpu_diag.txt) */
-gb_status gb_pr_shard_partition(const gb_graph* graph, uint32_t parts, uint32_t row_cost,
-                                const double* cuts, uint32_t* ranges);
-/* cuts == NULL: the greedy rule above.  Otherwise parts-1 increasing fractions in (0,1) of the total
- * weight at which the ranges are cut (measured-time rebalancing). */
-gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t row_begin, uint32_t row_end,
-                             gb_pr_shard** shard);
-gb_status gb_pr_shard_info(const gb_pr_shard* shard, uint32_t* row_begin, uint32_t* row_end,
-                           uint32_t* active_rows, uint64_t* edges);
+/* layout statistics of the single-GPU JACOBI plan (built on first use) */
+gb_status gb_page_rank_plan_info(const gb_graph* graph, gb_pr_shard_stats* stats);
+/* drops the cached layout (the next JACOBI call rebuilds it, re-reading the GB_PR_* experiment knobs) */
+gb_status gb_page_rank_plan_reset(const gb_graph* graph);
+/* builds the layout of shard `rank` of `world` on the graph's device */
+gb_status gb_pr_shard_create(const gb_graph* graph, uint32_t rank, uint32_t world, gb_pr_shard** shard);
+gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats);
 /* fills the full initial vectors (n floats each, internal order) on this rank: d_x0 = init/outdeg,
- * the constant part of d_x1, d_scores = init */
+ * the constant part of d_x1; d_scores = init for own rows, 0 for the others (rows without in-edges:
+ * base on rank 0), so that the ranks' score vectors can be summed into the full one */
 gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0, float* d_x1,
                            float* d_scores, void* cuda_stream);
-/* one sweep (1-based sweep_no) over the shard's rows: reads the full d_x_cur[n], writes
- * d_x_next[row_begin..row_end) and the same slice of every d_peer_x_next[i] (peer-mapped full
- * vectors; peer_count may be 0), updates d_scores[row_begin..row_end) and stores this shard's share
- * of the sweep error in *d_error.  All work is enqueued on cuda_stream (a cudaStream_t). */
+/* one sweep (1-based sweep_no) over the shard's rows: reads the full d_x_cur[n], writes the shard's
+ * entries of d_x_next and of every peer's next vector — through d_mc_x_next (a multicast mapping of
+ * all ranks' next vectors, this rank's included) when it is non-NULL, else through d_peer_x_next[i]
+ * (peer-mapped full vectors; peer_count may be 0) — updates the shard's entries of d_scores and stores
+ * this shard's share of the sweep error in *d_error.  All work is enqueued on cuda_stream. */
 gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t sweep_no,
                            const float* d_x_cur, float* d_x_next, float* const* d_peer_x_next,
-                           uint32_t peer_count, float* d_scores, double* d_error, void* cuda_stream);
+                           uint32_t peer_count, float* d_mc_x_next, float* d_scores, double* d_error,
+                           void* cuda_stream);
 /* internal order -> original ids: d_scores_out[v] = d_scores_internal[new_id[v]] */
 gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_internal,
                              float* d_scores_out, void* cuda_stream);

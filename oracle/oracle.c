@@ -384,6 +384,21 @@ static void* pr_mt_worker(void* p) {
   return NULL;
 }
 
+typedef struct {
+  const uint32_t* out_off;
+  float *out, *scores;
+  float init;
+  uint64_t begin, end;
+} pr_init_arg;
+static void* pr_init_worker(void* p) {
+  pr_init_arg* a = (pr_init_arg*)p;
+  for (uint64_t v = a->begin; v < a->end; ++v) {
+    a->out[v] = a->init / (float)(a->out_off[v + 1] - a->out_off[v]);
+    a->scores[v] = a->init;
+  }
+  return NULL;
+}
+
 ORC_API void orc_page_rank_mt(const uint32_t* in_off, const uint32_t* in_tgt,
                               const uint32_t* out_off, uint32_t n, uint64_t max_iterations,
                               double tolerance, float damping, int threads, float* scores,
@@ -393,12 +408,19 @@ ORC_API void orc_page_rank_mt(const uint32_t* in_off, const uint32_t* in_tgt,
   float init = 1.0f / nf;
   float base = (1.0f - damping) / nf;
   float* out = (float*)malloc((size_t)(n ? n : 1) * sizeof(float));
-  for (uint32_t v = 0; v < n; ++v) {
-    out[v] = init / (float)(out_off[v + 1] - out_off[v]);
-    scores[v] = init;
-  }
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)T);
   pr_mt_arg* args = (pr_mt_arg*)malloc(sizeof(pr_mt_arg) * (size_t)T);
+  { /* out_scores / scores initialised in parallel (par_iter, page_rank.rs:75-79) */
+    pr_init_arg* ia = (pr_init_arg*)malloc(sizeof(pr_init_arg) * (size_t)T);
+    for (int t = 0; t < T; ++t) {
+      pr_init_arg a = {out_off, out, scores, init, (uint64_t)n * (uint64_t)t / (uint64_t)T,
+                       (uint64_t)n * (uint64_t)(t + 1) / (uint64_t)T};
+      ia[t] = a;
+      pthread_create(&th[t], NULL, pr_init_worker, &ia[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+    free(ia);
+  }
   uint64_t it = 0;
   double err = 0.0;
   for (;;) {

@@ -29,12 +29,12 @@ def _worker(rank, world, port, scale, exchange, q):
             out.append((spr.ran_iterations, spr.error, spr.scores_host()))
         single = g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores() if rank == 0 else None
         if rank == 0:
-            q.put((spr.exchange, spr.ranges, out, single))
+            q.put((spr.exchange, spr.multicast, out, single))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["allgather", "peer"])
 def test_sharded_page_rank_matches_oracle(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -48,7 +48,7 @@ def test_sharded_page_rank_matches_oracle(exchange):
     procs = [ctx.Process(target=_worker, args=(r, world, port, scale, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
-    used, ranges, out, single = q.get()
+    used, multicast, out, single = q.get()
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0

@@ -246,6 +246,20 @@ def test_page_rank_edge_cases(gb):
         g.page_rank(max_iterations=0, tolerance=0.0)
 
 
+def test_page_rank_scale22_matches_oracle(gb):
+    """BASELINE.json configs[1]: RMAT scale-22, 20 sweeps, every rank within 1e-6 of the f64-accumulating
+    oracle on the same CSR (the device CSR build is checked against the oracle's separately)."""
+    g = gb.DiGraph.rmat(22, seed=42, layout=gb.Layout.Sorted)
+    ooff, _ = g.csr("out")
+    ioff, itgt = g.csr("in")
+    want, it, err = oracle.page_rank_jacobi(ioff, itgt, ooff, 20, 0.0, 0.85, acc64=True)
+    pr = g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi")
+    assert pr.ran_iterations == it == 20
+    rel = np.abs(pr.scores() - want) / want
+    assert rel.max() <= PR_RTOL, rel.max()
+    assert abs(pr.error - err) <= 4 * ERR_ATOL
+
+
 def test_page_rank_full_size_properties(gb):
     """BASELINE.json configs[1] size (RMAT scale-22, 20 sweeps): size-independent properties."""
     g = gb.DiGraph.rmat(22, seed=42, layout=gb.Layout.Sorted)
@@ -321,6 +335,8 @@ def test_wcc_full_size_properties(gb):
     srcs = np.repeat(np.arange(n, dtype=np.uint32), np.diff(ooff.astype(np.int64)))
     assert (comp[srcs] == comp[otgt]).all()                  # no edge crosses components
     assert (g.wcc(neighbor_rounds=1).components() == comp).all()
+    # bit-exact against the oracle at the stated size (the properties above cannot see over-merging)
+    assert (comp == oracle.wcc_min_label(ooff, otgt)).all()
 
 
 # ---- SSSP --------------------------------------------------------------------------------------
@@ -386,6 +402,20 @@ def test_triangle_count_bit_exact(gb, scale, layout):
     assert ug.global_triangle_count().triangles == oracle.triangle_count(noff, ntgt, threads=0)
 
 
+def test_triangle_count_scale22_matches_oracle(gb):
+    """BASELINE.json configs[3]: undirected RMAT scale-22, CsrLayout::Sorted — the count of the raw graph
+    and of the degree-ordered graph, bit-exact against the multi-threaded oracle on the same CSR."""
+    ug = gb.Graph.rmat(22, seed=42, layout=gb.Layout.Sorted)
+    off, tgt = (a.copy() for a in ug.csr())   # copies: live views would block the relabelling below
+    if oracle.hardware_threads() >= 16:     # the raw Sorted count is ~1e11 merge steps on the CPU
+        assert ug.global_triangle_count().triangles == oracle.triangle_count(off, tgt, threads=0)
+    ug.make_degree_ordered()
+    noff, ntgt = ug.csr()
+    want_off, want_tgt, _ = oracle.make_degree_ordered(off, tgt)
+    assert (noff == want_off).all() and (ntgt == want_tgt).all()
+    assert ug.global_triangle_count().triangles == oracle.triangle_count(noff, ntgt, threads=0)
+
+
 def test_wrong_graph_kind_is_rejected(gb):
     e = np.array([[0, 1], [1, 2]], dtype=np.uint32)
     import ctypes as C
@@ -431,25 +461,23 @@ def test_invalid_host_csr_is_rejected(gb):
         gb.DiGraph.from_numpy(np.array([[0, 9]], dtype=np.uint32), node_count=4)
 
 
-# ---- shard API on one GPU: several virtual ranks, slices exchanged by plain copies ---------------
-@pytest.mark.parametrize("world,cuts", [(2, None), (3, [0.2, 0.7]), (4, [1e-6, 0.5, 0.999999]), (8, None)])
-def test_shard_api_virtual_ranks_match_single_gpu(gb, world, cuts):
+# ---- shard API on one GPU: several virtual ranks, dealt slices exchanged by plain copies ----------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_api_virtual_ranks_match_single_gpu(gb, world):
     import torch
-    from graph_b200.multigpu import CudaShardBackend
+    from graph_b200.multigpu import CudaShardBackend, owner_of_rows
     g = gb.DiGraph.rmat(15, seed=11, layout=gb.Layout.Sorted)
     n = g.node_count()
     sweeps, damping = 6, 0.85
     want = g.page_rank(max_iterations=sweeps, tolerance=0.0, damping_factor=damping, mode="jacobi")
-    ranks = [CudaShardBackend(g, r, world, row_cost=5) for r in range(world)]
-    if cuts is not None:
-        for b in ranks:
-            b.repartition(cuts)
-    ranges = ranks[0].ranges
-    assert all(b.ranges == ranges for b in ranks) and ranges[0] == 0 and ranges[-1] == n
-    assert all(ranges[i] <= ranges[i + 1] for i in range(world))
+    ranks = [CudaShardBackend(g, r, world) for r in range(world)]
     n_active = ranks[0].n_active
+    assert sum(b.stats["local_rows"] for b in ranks) == n_active
+    assert sum(b.stats["local_edges"] for b in ranks) == g.edge_count()
     dev = ranks[0].device
-    x = [[torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(world)]
+    owner = torch.from_numpy(owner_of_rows(np.arange(n), world)).to(dev)
+    mine = [owner == r for r in range(world)]
+    x = [[torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(world)]
     scores = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(world)]
     err = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
     for r, b in enumerate(ranks):
@@ -460,16 +488,40 @@ def test_shard_api_virtual_ranks_match_single_gpu(gb, world, cuts):
         for r, b in enumerate(ranks):
             b.step(damping, sweep, x[r][cur], x[r][nxt], None, scores[r], err[r])
         torch.cuda.synchronize()
-        for r in range(world):  # the all-gather: every rank's slice goes to every other rank
-            lo, hi = min(ranges[r], n_active), min(ranges[r + 1], n_active)
+        for r in range(world):  # the all-gather: every rank's rows go to every other rank
             for q in range(world):
-                if q != r and hi > lo:
-                    x[q][nxt][lo:hi].copy_(x[r][nxt][lo:hi])
+                if q != r:
+                    x[q][nxt][mine[r]] = x[r][nxt][mine[r]]
         total = sum(float(e.item()) for e in err)
-    for r in range(world):
-        lo, hi = min(ranges[r], n_active), min(ranges[r + 1], n_active)
-        if hi > lo:
-            scores[0][lo:hi].copy_(scores[r][lo:hi])
-    got = ranks[0].finish(scores[0]).cpu().numpy()
-    assert got.tobytes() == want.scores().tobytes()   # one lane per row / segment: sharding cannot change a sum
-    assert abs(total - want.error) <= 1e-9 + 1e-9 * want.error
+    full = torch.stack(scores).sum(dim=0)   # own rows + zeros elsewhere (rows without in-edges: rank 0)
+    got = ranks[0].finish(full).cpu().numpy()
+    # every (row, block) partial is the same set of addends on every shard count; only the tree that
+    # adds a pair's 4-id groups depends on where the pair sits in its 32-group step: <= 1 ulp per partial
+    assert np.max(np.abs(got - want.scores()) / want.scores()) <= 5e-7
+    assert abs(total - want.error) <= 1e-7 + 1e-6 * want.error
+
+
+# ---- column-block layout under stress: tiny blocks / chunks so that segments are cut by chunk and
+# step boundaries, several hot blocks, the fixup path -------------------------------------------------
+@pytest.mark.parametrize("block,chunk,tau", [(1024, 32, 1.0), (4096, 64, 2.0), (2048, 32, 0.5), (32768, 0, 1e9)])
+def test_page_rank_column_block_knobs(gb, monkeypatch, block, chunk, tau):
+    monkeypatch.setenv("GB_PR_BLOCK", str(block))
+    monkeypatch.setenv("GB_PR_CHUNK", str(chunk))
+    monkeypatch.setenv("GB_PR_TAU", str(tau))
+    src, dst = oracle.rmat_edges(16, seed=5)
+    n = 1 << 16
+    out, inc = oracle_digraph(src, dst, n, oracle.SORTED)
+    g = gb.DiGraph.from_csr(out[0], out[1], inc[0], inc[1])
+    info = g.page_rank_plan_info()
+    if tau < 100:
+        assert info["hot_blocks"] > 1 and info["block_edges"] > 0.5 * info["local_edges"]
+        if chunk == 32:
+            assert info["cut_segments"] > 0          # the hub rows' segments span several chunks
+    else:
+        assert info["hot_blocks"] == 0 and info["block_edges"] == 0   # everything through SELL
+    want, it, err = oracle.page_rank_jacobi(inc[0], inc[1], out[0], 20, 0.0, 0.85)
+    pr = g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi")
+    rel = np.abs(pr.scores() - want) / want
+    assert rel.max() <= PR_RTOL, rel.max()
+    assert abs(pr.error - err) <= ERR_ATOL
+    assert g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores().tobytes() == pr.scores().tobytes()
