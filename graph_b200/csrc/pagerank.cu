@@ -111,6 +111,11 @@ struct PrPlan {
   DevBuf<float> x[2];
   DevBuf<float> scores;
   unsigned grid_cb = 0, grid_sell = 0, grid_fin = 1;
+  uint32_t n_fin_warp = 0;   // rows [0, n_fin_warp) own segments in more than 32 blocks
+  // dual mode: k_pr_cb and k_pr_sell run at the same time on the same SMs (two streams, 512-thread CTAs)
+  bool dual = false;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf<double> block_err;  // per CTA error partials (SELL CTAs, then finish CTAs)
   DevBuf<double> err_hist;   // error of each sweep of the current batch
   DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
@@ -128,6 +133,9 @@ struct PrPlan {
 void free_pr_plan(PrPlan* p) {
   if (!p) return;
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->s2) cudaStreamDestroy(p->s2);
   delete p;
 }
 uint64_t pr_plan_bytes(const PrPlan* p) { return p ? p->bytes() : 0; }
@@ -458,6 +466,7 @@ struct PrArgs {
   float* scores;
   PrDeal deal;
   uint32_t n_loc, n_cb;
+  uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in more than 32 blocks (finish: one warp each)
   // column blocks
   uint32_t B, KB;
   const uint32_t* blk;
@@ -497,33 +506,48 @@ struct PrArgs {
 // the previous one; and every pending miss holds an L1 line, so the hot head must leave L1 room —
 // at 208 KB of shared memory (16 KB of L1) the sweep ran 2.8x slower than at 128 KB (96 KB of L1);
 // ld.global.nc.L1::no_allocate was slower still at every size.
+template <bool HOT>
 __device__ __forceinline__ void pr_gather(const float* x, uint32_t hot_saddr, uint32_t hot_n,
                                           const uint4& ta, const uint4& tb, float (&v)[8]) {
   const uint32_t t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
   float vs[8], vg[8];
+  if (HOT) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.lt.u32 p, %1, %2;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t"
-        "@p ld.shared.f32 %0, [%3];\n\t}"
-        : "=f"(vs[j])
-        : "r"(t[j]), "r"(hot_n), "r"(hot_saddr + 4u * t[j]));
+    for (int j = 0; j < 8; ++j) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.lt.u32 p, %1, %2;\n\t"
+          "mov.f32 %0, 0f00000000;\n\t"
+          "@p ld.shared.f32 %0, [%3];\n\t}"
+          : "=f"(vs[j])
+          : "r"(t[j]), "r"(hot_n), "r"(hot_saddr + 4u * t[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ge.u32 p, %1, %2;\n\t"
+          "setp.ne.and.u32 p, %1, 0xffffffff, p;\n\t"
+          "mov.f32 %0, 0f00000000;\n\t"
+          "@p ld.global.nc.f32 %0, [%3];\n\t}"
+          : "=f"(vg[j])
+          : "r"(t[j]), "r"(hot_n), "l"(x + t[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = vs[j] + vg[j];
+  } else {
+    // no shared-memory mirror (the SELL kernel shares its SM with the column-block kernel)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+          "mov.f32 %0, 0f00000000;\n\t"
+          "@p ld.global.nc.f32 %0, [%2];\n\t}"
+          : "=f"(v[j])
+          : "r"(t[j]), "l"(x + t[j]));
+    }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ge.u32 p, %1, %2;\n\t"
-        "setp.ne.and.u32 p, %1, 0xffffffff, p;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t"
-        "@p ld.global.nc.f32 %0, [%3];\n\t}"
-        : "=f"(vg[j])
-        : "r"(t[j]), "r"(hot_n), "l"(x + t[j]));
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = vs[j] + vg[j];
 }
 __device__ __forceinline__ float pr_sum8(const float (&v)[8]) {
   return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
@@ -548,59 +572,101 @@ __device__ __forceinline__ double pr_update(uint32_t gr, float sum, float old, u
 }
 
 // ---- column blocks ------------------------------------------------------------------------------------
-// One warp, one chunk: groups [g0, g1) of block j's stream, 32 groups (128 ids) per step.  Lanes of a
-// step that belong to the same row are combined by a segmented inclusive scan; a segment that spans
-// steps is carried in f64.  The row of a lane follows from counting segment-start bits.
-__device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint32_t c, uint32_t lane, uint32_t pad2) {
-  const uint4 ch = a.chunks[c];
+// One warp, one chunk: groups [g0, g1) of block j's stream, 64 groups (256 ids) per step.  Lane L owns
+// the ADJACENT groups 2L and 2L+1 of the even-aligned window (one 128-bit load).  Inside a lane the two
+// group sums are combined when they belong to the same row; across lanes the value of the run that is
+// open at the end of each lane goes through a segmented inclusive scan (5 shuffles per 256 ids); a run
+// that spans steps is carried in f64.  The row of a group follows from counting segment-start bits.
+// A lane ends at most two runs per step: the one its first group closes and the one open at its end.
+// SPECIAL = the chunk starts or ends inside a segment (rare: segments longer than a chunk); the common
+// instantiation carries none of the side-buffer logic.
+template <bool SPECIAL>
+__device__ __forceinline__ void cb_emit(const PrArgs& a, uint32_t c, bool is_end, uint32_t q, uint32_t last,
+                                        bool run_continues, bool last_step, bool tail_cont, bool in_head,
+                                        uint32_t cum, uint32_t slot0, double tot) {
+  if (!is_end) return;
+  if (SPECIAL) {
+    if (q == last && run_continues && !last_step) return;  // carried into the next step
+    if (in_head && cum == 0) a.side[2 * (size_t)c] = tot;                        // tail part of a cut segment
+    else if (q == last && last_step && tail_cont) a.side[2 * (size_t)c + 1] = tot;  // head part of one
+    else a.partial[slot0 + cum] = (float)tot;
+  } else {
+    if (q == last && run_continues) return;  // carried into the next step
+    a.partial[slot0 + cum] = (float)tot;
+  }
+}
+template <bool SPECIAL>
+__device__ __forceinline__ void cb_chunk_impl(const PrArgs& a, const float* xs, uint32_t c, const uint4 ch,
+                                              uint32_t lane, uint32_t pad2) {
   const uint32_t g0 = ch.x, g1 = ch.y;
-  if (g0 >= g1) return;
-  uint32_t row_before = ch.z;
   const uint32_t j = ch.w & 0xFFFFFFu, fl = ch.w >> 24;
-  const bool head_cont = fl & CB_HEAD_CONT, tail_cont = fl & CB_TAIL_CONT;
-  float* __restrict__ partial = a.partial + a.poff[j];
+  const bool head_cont = SPECIAL && (fl & CB_HEAD_CONT), tail_cont = SPECIAL && (fl & CB_TAIL_CONT);
+  uint32_t slot0 = a.poff[j] + ch.z;  // staircase slot of the row "before" the first segment start
   bool in_head = head_cont;
   double carry = 0.0;
-  uint2 ids = make_uint2(pad2, pad2);
-  if (g0 + lane < g1) ids = ld_stream_u2(a.cb_ids + g0 + lane);
   const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
-  for (uint32_t gs = g0; gs < g1; gs += 32) {
-    uint2 nids = make_uint2(pad2, pad2);
-    if (gs + 32 + lane < g1) nids = ld_stream_u2(a.cb_ids + gs + 32 + lane);
+  const uint32_t ia = 2 * lane, ib = ia + 1;
+  const uint4* ids16 = reinterpret_cast<const uint4*>(a.cb_ids);  // pairs of groups
+  const uint4 padv = make_uint4(pad2, pad2, pad2, pad2);
+  const uint32_t gs0 = g0 & ~1u;
+  uint4 ids = padv;
+  if (gs0 + ia < g1) ids = ld_stream_u4(reinterpret_cast<const uint32_t*>(ids16 + (gs0 >> 1) + lane));
+  for (uint32_t gs = gs0; gs < g1; gs += 64) {
+    uint4 nids = padv;
+    if (gs + 64 + ia < g1) nids = ld_stream_u4(reinterpret_cast<const uint32_t*>(ids16 + ((gs + 64) >> 1) + lane));
+    // groups outside [g0, g1) belong to the neighbouring chunks
+    if (gs + ia < g0) ids.x = ids.y = pad2;
+    if (gs + ib >= g1) ids.z = ids.w = pad2;
     const uint32_t wi = gs >> 5, sh = gs & 31u;
-    const uint32_t w0 = __ldg(a.cb_bits + wi), w1 = __ldg(a.cb_bits + wi + 1);
-    uint32_t flags = __funnelshift_r(w0, w1, sh);
-    const uint32_t nvalid = min(32u, g1 - gs);
-    if (nvalid < 32) flags &= (1u << nvalid) - 1u;
-    const bool last_step = gs + 32 >= g1;
-    // does the run of the last valid lane go on after this step (inside the chunk / past its end)?
-    const bool run_continues = last_step ? tail_cont : !((w1 >> sh) & 1u);
-    float v = (xs[ids.x & 0xFFFFu] + xs[ids.x >> 16]) + (xs[ids.y & 0xFFFFu] + xs[ids.y >> 16]);
-    const uint32_t below = flags & le_mask;
+    const uint32_t w0 = __ldg(a.cb_bits + wi), w1 = __ldg(a.cb_bits + wi + 1), w2 = __ldg(a.cb_bits + wi + 2);
+    unsigned long long W = ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+    const uint32_t nvalid = min(64u, g1 - gs);
+    if (nvalid < 64) W &= (1ull << nvalid) - 1ull;
+    if (gs < g0) W &= ~1ull;
+    const uint32_t last = nvalid - 1;
+    const bool last_step = gs + 64 >= g1;
+    // does the run of the last valid group go on after this step (inside the chunk / past its end)?
+    const bool run_continues = last_step ? tail_cont : !((w2 >> sh) & 1u);
+    const float va = xs[ids.x & 0xFFFFu] + xs[ids.x >> 16] + (xs[ids.y & 0xFFFFu] + xs[ids.y >> 16]);
+    const float vb = xs[ids.z & 0xFFFFu] + xs[ids.z >> 16] + (xs[ids.w & 0xFFFFu] + xs[ids.w >> 16]);
+    const uint32_t pair = (uint32_t)(W >> ia) & 3u;
+    const bool fa = pair & 1u, fb = pair & 2u;
+    float incl = fb ? vb : va + vb;  // this lane's share of the run open at its end
+    const uint32_t below = __ballot_sync(0xFFFFFFFFu, pair != 0) & le_mask;
     const int seg_start = below ? 31 - __clz(below) : -1;
     const int lo = seg_start < 0 ? 0 : seg_start;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const float t = __shfl_up_sync(0xFFFFFFFFu, v, d);
-      if ((int)lane - d >= lo) v += t;
+      const float t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((int)lane - d >= lo) incl += t;
     }
-    const uint32_t last = nvalid - 1;
-    const bool is_end = lane < nvalid && (lane == last || ((flags >> (lane + 1)) & 1u));
-    const double tot = (double)v + (seg_start < 0 ? carry : 0.0);
-    if (is_end && !(lane == last && run_continues && !last_step)) {
-      if (in_head && seg_start < 0) a.side[2 * (size_t)c] = tot;              // tail part of a cut segment
-      else if (lane == last && last_step && tail_cont) a.side[2 * (size_t)c + 1] = tot;  // head part of one
-      else partial[row_before + __popc(below)] = (float)tot;
-    }
-    const double tl = __shfl_sync(0xFFFFFFFFu, tot, last);
+    const double incl_d = (double)incl + (seg_start < 0 ? carry : 0.0);
+    double x_in = __shfl_up_sync(0xFFFFFFFFu, incl_d, 1);  // the run open at the end of the previous lane
+    if (lane == 0) x_in = carry;
+    const uint32_t cum_a = __popcll(W & ((2ull << ia) - 1ull));  // segment starts at positions <= ia
+    const uint32_t cum_b = cum_a + (fb ? 1u : 0u);
+    const bool valid_a = gs + ia >= g0 && ia <= last, valid_b = ib <= last;
+    const bool nxt = ib < 63 ? ((W >> (ib + 1)) & 1ull) != 0 : false;
+    cb_emit<SPECIAL>(a, c, valid_a && (ia == last || fb), ia, last, run_continues, last_step, tail_cont, in_head,
+                     cum_a, slot0, (fa ? 0.0 : x_in) + (double)va);
+    cb_emit<SPECIAL>(a, c, valid_b && (ib == last || nxt), ib, last, run_continues, last_step, tail_cont, in_head,
+                     cum_b, slot0, incl_d);
+    const double tl = __shfl_sync(0xFFFFFFFFu, incl_d, 31);
     carry = (run_continues && !last_step) ? tl : 0.0;
-    if (flags) in_head = false;
-    row_before += __popc(flags);
+    if (SPECIAL && W) in_head = false;
+    slot0 += __popcll(W);
     ids = nids;
   }
 }
+__device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint32_t c, uint32_t lane, uint32_t pad2) {
+  const uint4 ch = a.chunks[c];
+  if (ch.x >= ch.y) return;
+  if ((ch.w >> 24) & (CB_HEAD_CONT | CB_TAIL_CONT)) cb_chunk_impl<true>(a, xs, c, ch, lane, pad2);
+  else cb_chunk_impl<false>(a, xs, c, ch, lane, pad2);
+}
 
-__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) {
+template <int NT>
+__device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
   __shared__ uint32_t s_task;
@@ -620,7 +686,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) {
     if (j != cur_j) {
       const uint64_t x0 = (uint64_t)a.blk[j] * B;
       const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
-      for (uint32_t i = threadIdx.x * 4; i < B; i += PR_THREADS * 4) {
+      for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (x0 + i + 3 < a.n) {
           v = __ldg(src + i / 4);
@@ -635,24 +701,18 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) {
       cur_j = j;
       __syncthreads();
     }
-    for (uint32_t c = task.x + warp; c < task.y; c += PR_WARPS) cb_chunk(a, xs, c, lane, pad2);
+    for (uint32_t c = task.x + warp; c < task.y; c += NT / 32) cb_chunk(a, xs, c, lane, pad2);
   }
 }
+__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb_body<PR_THREADS>(a); }
+// dual mode: 512 threads and at most 56 registers, so that a 512-thread k_pr_sell CTA (64 registers)
+// fits beside it on the SM
+__global__ void __maxnreg__(56) k_pr_cb_half(const PrArgs a) { pr_cb_body<PR_THREADS / 2>(a); }
 
-// ---- SELL-32 sweep: one lane per row ------------------------------------------------------------
-// A lane reads its row four targets at a time (128-bit, coalesced: the slice is stored group-major,
-// lane-minor), gathers, and adds in row order.  The next slice's first targets and row metadata are
-// requested while the current slice is processed.  Rows below n_cb only hold the edges that are not in
-// a column-block segment: their sum goes to rem[] and the finish kernel completes them.
-// Prologue: segments cut by chunk boundaries get their parts added in a fixed order (the column-block
-// kernel ran before this one on the stream).
-template <bool PEERS>
-__global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* hot = smem;
-  __shared__ double warp_err[PR_WARPS];
+// segments cut by chunk boundaries: their parts are added in a fixed order (tiny; after k_pr_cb)
+__global__ void k_pr_fixup(const PrArgs a) {
   if (a.ctrl[0] != 0) return;
-  for (uint32_t i = blockIdx.x * PR_THREADS + threadIdx.x; i < a.n_fix; i += gridDim.x * PR_THREADS) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_fix; i += gridDim.x * blockDim.x) {
     const uint32_t c0 = a.fix_list[i];
     double t = a.side[2 * (size_t)c0 + 1];
     uint32_t k = c0 + 1;
@@ -663,18 +723,39 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
     }
     a.partial[a.tail_slot[c0]] = (float)t;
   }
+}
+
+// ---- SELL-32 sweep: one lane per row ------------------------------------------------------------
+// A lane reads its row four targets at a time (128-bit, coalesced: the slice is stored group-major,
+// lane-minor), gathers, and adds in row order.  The next slice's first targets and row metadata are
+// requested while the current slice is processed.  Rows below n_cb only hold the edges that are not in
+// a column-block segment: their sum goes to rem[] and the finish kernel completes them.
+// HOT: mirror the first hot_count sources in shared memory (used when this kernel has the SM to
+// itself); without it the kernel needs no shared memory and runs beside k_pr_cb on the same SMs —
+// the column blocks are bound by the shared-memory pipe and issue slots, this kernel by the
+// L1TEX->XBAR request port, so the two overlap.
+template <bool PEERS, bool HOT, int NT>
+__global__ void __launch_bounds__(NT, HOT ? 1 : 2048 / NT / 2) k_pr_sell(const PrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* hot = smem;
+  constexpr int NW = NT / 32;
+  __shared__ double warp_err[NW];
+  if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ x = a.x_cur;
-  const uint32_t hot_n = a.hot_count;
-  for (uint32_t i = threadIdx.x * 4; i < hot_n; i += PR_THREADS * 4)
-    *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
-  __syncthreads();
-  const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
+  const uint32_t hot_n = HOT ? a.hot_count : 0;
+  uint32_t hot_saddr = 0;
+  if (HOT) {
+    for (uint32_t i = threadIdx.x * 4; i < hot_n; i += NT * 4)
+      *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
+    __syncthreads();
+    hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
+  }
   double err = 0.0;
-  const uint32_t stride = gridDim.x * PR_WARPS;
+  const uint32_t stride = gridDim.x * NW;
   const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
   const uint32_t P = a.deal.P, pp = a.deal.p;
-  uint32_t sidx = blockIdx.x * PR_WARPS + warp;
+  uint32_t sidx = blockIdx.x * NW + warp;
   // pipeline state: metadata of this and the next slice, first two target groups + row data of this one
   uint2 meta = make_uint2(0, 0), nmeta = meta;
   uint4 ta = pad, tb = pad;
@@ -721,7 +802,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
       const uint4 na = (q + 2 < w4) ? pr_ld4(base + (q + 2) * 32) : pad;
       const uint4 nb = (q + 3 < w4) ? pr_ld4(base + (q + 3) * 32) : pad;
       float v[8];
-      pr_gather(x, hot_saddr, hot_n, ta, tb, v);
+      pr_gather<HOT>(x, hot_saddr, hot_n, ta, tb, v);
       acc += pr_sum8(v);
       ta = na;
       tb = nb;
@@ -742,14 +823,25 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_sell(const PrArgs a) {
   if (threadIdx.x == 0) {
     double tt = 0.0;
 #pragma unroll
-    for (int w = 0; w < PR_WARPS; ++w) tt += warp_err[w];
+    for (int w = 0; w < NW; ++w) tt += warp_err[w];
     a.block_err[blockIdx.x] = tt;
   }
 }
 
 // ---- finish: rows with segments = partials of their blocks (fixed order, f64) + SELL remainder -----
-// One lane per row; the last CTA to finish reduces all CTA error partials in a fixed order and
-// evaluates the stop rule of page_rank.rs:107 on the device.
+// Rows that own segments in more than 32 blocks (the hubs: a prefix) get one warp each, lanes striding
+// over the blocks; all other rows one lane each with at most 32 independent loads.  The last CTA to
+// finish reduces all CTA error partials in a fixed order and evaluates the stop rule of
+// page_rank.rs:107 on the device.
+__device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __restrict__ nrows, uint32_t KB, uint32_t l) {
+  uint32_t lo = 0, hi = KB;  // first j with nrows[j] <= l  (nrows is non-increasing)
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) / 2;
+    if (__ldg(nrows + mid) > l) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
 template <bool PEERS>
 __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   constexpr int FIN_WARPS = PR_FIN_THREADS / 32;
@@ -760,12 +852,25 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
   double err = 0.0;
   const uint32_t P = a.deal.P, pp = a.deal.p;
-  for (uint32_t l0 = (blockIdx.x * FIN_WARPS + warp) * 32; l0 < a.n_cb; l0 += gridDim.x * FIN_WARPS * 32) {
-    const uint32_t l = l0 + lane;
+  const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
+  // hub rows: one warp per row
+  for (uint32_t l = gw; l < a.n_fin_warp; l += nw) {
+    const uint32_t kb = fin_blocks_of(a.nrows, a.KB, l);
+    double s = 0.0;
+    for (uint32_t j = lane; j < kb; j += 32) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const uint32_t gr = deal_global(l, P, pp);
+      err += pr_update<PEERS>(gr, (float)(s + (double)a.rem[l]), a.scores[gr], a.outdeg[gr], a);
+    }
+  }
+  // all other rows with segments: one lane per row, at most 32 blocks each
+  const uint32_t tail_warps = (a.n_cb - a.n_fin_warp + 31) / 32;
+  for (uint32_t w = gw; w < tail_warps; w += nw) {
+    const uint32_t l0 = a.n_fin_warp + 32 * w, l = l0 + lane;
     const bool on = l < a.n_cb;
     float old = 0.0f;
-    uint32_t deg = 1;
-    uint32_t gr = 0;
+    uint32_t deg = 1, gr = 0;
     double s = 0.0;
     if (on) {
       gr = deal_global(l, P, pp);
@@ -773,12 +878,10 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
       deg = a.outdeg[gr];
       s = (double)a.rem[l];
     }
-    // nrows[] is non-increasing: the first block whose prefix ends at or before l0 ends the loop
-    for (uint32_t j = 0; j < a.KB; ++j) {
-      const uint32_t nr = __ldg(a.nrows + j);
-      if (nr <= l0) break;
-      if (l < nr) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
-    }
+    const uint32_t kb = fin_blocks_of(a.nrows, a.KB, l0);  // the warp's first row has the most blocks
+#pragma unroll 4
+    for (uint32_t j = 0; j < kb; ++j)
+      if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     if (on) err += pr_update<PEERS>(gr, (float)s, old, deg, a);
   }
   err = warp_sum(err);
@@ -1162,12 +1265,25 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     p->smem_sell = (size_t)p->hot_count * sizeof(float) + 16;
     p->smem_cb = ((size_t)B + 4) * sizeof(float);
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sell));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sell));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_cb_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false, true, PR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p->smem_sell));
+    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true, true, PR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p->smem_sell));
+    // dual mode needs both kernels to have work; GB_PR_DUAL=0 runs them back to back on one stream
+    p->dual = p->n_tasks > 0 && p->num_slices > 0 && env_u32("GB_PR_DUAL", 1) != 0;
+    if (p->dual) {
+      GB_CUDA(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+      GB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      GB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
     p->grid_cb = (unsigned)std::min<uint64_t>(p->n_tasks, (uint64_t)dev_sms);  // one persistent CTA per SM
-    const uint64_t want_sell = ((uint64_t)p->num_slices + PR_WARPS - 1) / PR_WARPS;
-    p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms);
-    const uint64_t want_fin = ((uint64_t)p->n_cb + PR_FIN_THREADS - 1) / PR_FIN_THREADS;
+    const uint32_t sell_warps = p->dual ? PR_WARPS / 2 : PR_WARPS;
+    const uint64_t want_sell = ((uint64_t)p->num_slices + sell_warps - 1) / sell_warps;
+    p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * (p->dual ? 2 : 1));
+    p->n_fin_warp = p->KB > 32 ? std::min<uint32_t>(p->n_cb, (h_nrows[32] + 31) / 32 * 32) : 0;
+    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp + (p->n_cb - p->n_fin_warp + 31) / 32;
+    const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
     const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
     GB_TRY(p->block_err.alloc(nerr));
@@ -1193,6 +1309,7 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.deal = p->deal;
   a.n_loc = p->n_loc;
   a.n_cb = p->n_cb;
+  a.n_fin_warp = p->n_fin_warp;
   a.B = p->B;
   a.KB = p->KB;
   a.blk = p->blk.p;
@@ -1226,20 +1343,35 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   return a;
 }
 
-// one sweep = column blocks, SELL rows (+ fixup of cut segments), finish; returns the launches made
+// one sweep = column blocks (+ fixup of cut segments) and SELL rows — at the same time in dual mode —
+// then finish; *launches is advanced by the kernels launched
 template <bool PEERS>
-static unsigned launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s) {
-  unsigned launches = 1;
-  if (p->grid_cb) {
-    k_pr_cb<<<p->grid_cb, PR_THREADS, p->smem_cb, s>>>(a);
-    ++launches;
-  }
-  if (p->grid_sell) {
-    k_pr_sell<PEERS><<<p->grid_sell, PR_THREADS, p->smem_sell, s>>>(a);
-    ++launches;
+static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, uint64_t* launches) {
+  const unsigned fix_grid = grid_for(p->n_fix, 128, 64);
+  if (p->dual) {
+    GB_CUDA(cudaEventRecord(p->ev_fork, s));
+    GB_CUDA(cudaStreamWaitEvent(p->s2, p->ev_fork, 0));
+    k_pr_cb_half<<<p->grid_cb, PR_THREADS / 2, p->smem_cb, s>>>(a);
+    k_pr_sell<PEERS, false, PR_THREADS / 2><<<p->grid_sell, PR_THREADS / 2, 0, p->s2>>>(a);
+    if (p->n_fix) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
+    GB_CUDA(cudaEventRecord(p->ev_join, p->s2));
+    GB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    *launches += 2 + (p->n_fix ? 1 : 0);
+  } else {
+    if (p->grid_cb) {
+      k_pr_cb<<<p->grid_cb, PR_THREADS, p->smem_cb, s>>>(a);
+      if (p->n_fix) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
+      *launches += 1 + (p->n_fix ? 1 : 0);
+    }
+    if (p->grid_sell) {
+      k_pr_sell<PEERS, true, PR_THREADS><<<p->grid_sell, PR_THREADS, p->smem_sell, s>>>(a);
+      *launches += 1;
+    }
   }
   k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
-  return launches;
+  *launches += 1;
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
 }
 
 // ---- drivers ---------------------------------------------------------------------------------
@@ -1319,7 +1451,7 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
         ev_used += 2;
         GB_CUDA(cudaEventRecord(e0, s));
       }
-      g->timing.kernel_launches += launch_sweep<false>(p, a, s);
+      GB_TRY(launch_sweep<false>(p, a, s, &g->timing.kernel_launches));
       if (e1) GB_CUDA(cudaEventRecord(e1, s));
       if (sweep_no == 1 && p->n_active < n) {
         // sources without in-edges change exactly once (init/deg -> base/deg): patch the buffer
@@ -1479,8 +1611,9 @@ gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t swe
   a.extra_err = (sweep_no == 1 && p->deal.p == 0)
                     ? (double)(p->n - p->n_active) * fabs((double)(base - init))
                     : 0.0;
-  if (peer_count || d_mc_x_next) gb::launch_sweep<true>(p, a, s);
-  else gb::launch_sweep<false>(p, a, s);
+  uint64_t launches = 0;
+  if (peer_count || d_mc_x_next) GB_TRY(gb::launch_sweep<true>(p, a, s, &launches));
+  else GB_TRY(gb::launch_sweep<false>(p, a, s, &launches));
   if (sweep_no == 1 && p->n_active < p->n)
     gb::k_pr_fill_inactive<<<gb::grid_for(p->n - p->n_active, 256), 256, 0, s>>>(
         p->n, p->n_active, base, p->outdeg.p, const_cast<float*>(d_x_cur));
@@ -1517,7 +1650,7 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
   stats->tasks = p->n_tasks;
   stats->cut_segments = p->n_fix;
   stats->chunk_groups = p->chunk_groups;
-  stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0);
+  stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) + (p->grid_cb && p->n_fix ? 1 : 0);
   stats->device_bytes = p->bytes();
   return GB_OK;
 }

@@ -59,7 +59,8 @@ def build_chunks(goff, poff, nrows, gbeg, C):
 
 
 def run_chunk(c, chunks, vals, bits, poff, partial, side):
-    """cb_chunk: vals[g] = f32 sum of group g's four gathers; bits[g] = group g starts a segment."""
+    """cb_chunk: vals[g] = f32 sum of group g's four gathers; bits[g] = group g starts a segment.
+    A step covers 64 groups; lane L owns the adjacent groups 2L and 2L+1 of the (even-aligned) window."""
     g0, g1, row_before, j, fl = chunks[c]
     if g0 >= g1:
         return
@@ -67,47 +68,64 @@ def run_chunk(c, chunks, vals, bits, poff, partial, side):
     in_head = head_cont
     carry = 0.0
     lanes = np.arange(32)
-    for gs in range(g0, g1, 32):
-        nvalid = min(32, g1 - gs)
-        flags = np.zeros(32, bool)
-        flags[:nvalid] = bits[gs:gs + nvalid]
-        last_step = gs + 32 >= g1
-        run_continues = tail_cont if last_step else (not bits[gs + 32])
-        v = np.zeros(32, np.float32)
-        v[:nvalid] = vals[gs:gs + nvalid]
-        below_cnt = np.cumsum(flags)                      # popc(below)
+    gs0 = g0 & ~1
+    for gs in range(gs0, g1, 64):
+        pos = np.arange(64)
+        valid = (gs + pos >= g0) & (gs + pos < g1)
+        W = np.zeros(64, bool)
+        W[valid] = bits[gs + pos[valid]]
+        v = np.zeros(64, np.float32)
+        v[valid] = vals[gs + pos[valid]]
+        last = int(np.nonzero(valid)[0][-1])
+        last_step = gs + 64 >= g1
+        run_continues = tail_cont if last_step else (not bits[gs + 64])
+        fa, fb = W[0::2], W[1::2]
+        va, vb = v[0::2], v[1::2]
+        T = np.where(fb, vb, (va + vb).astype(np.float32)).astype(np.float32)
+        F = fa | fb
         seg_start = np.full(32, -1)
         cur = -1
         for l in range(32):
-            if flags[l]:
+            if F[l]:
                 cur = l
             seg_start[l] = cur
         lo = np.maximum(seg_start, 0)
+        incl = T.copy()
         d = 1
         while d < 32:
             t = np.zeros(32, np.float32)
-            t[d:] = v[:-d]
+            t[d:] = incl[:-d]
             add = (lanes - d) >= lo
-            v = np.where(add, (v + t).astype(np.float32), v)
+            incl = np.where(add, (incl + t).astype(np.float32), incl)
             d <<= 1
-        last = nvalid - 1
-        tot = v.astype(np.float64) + np.where(seg_start < 0, carry, 0.0)
-        for l in range(nvalid):
-            is_end = l == last or flags[l + 1] if l + 1 < 32 else True
-            if not is_end:
-                continue
-            if l == last and run_continues and not last_step:
-                continue
-            if in_head and seg_start[l] < 0:
-                side[2 * c] = tot[l]
-            elif l == last and last_step and tail_cont:
-                side[2 * c + 1] = tot[l]
-            else:
-                partial[poff[j] + row_before + below_cnt[l]] = np.float32(tot[l])
-        carry = tot[last] if (run_continues and not last_step) else 0.0
-        if flags.any():
+        inclD = incl.astype(np.float64) + np.where(seg_start < 0, carry, 0.0)
+        XD = np.empty(32)
+        XD[0] = carry
+        XD[1:] = inclD[:-1]
+        cum = np.cumsum(W)                 # starts at positions <= q
+        for l in range(32):
+            ia, ib = 2 * l, 2 * l + 1
+            tot_a = (0.0 if fa[l] else XD[l]) + float(va[l])
+            tot_b = inclD[l]
+            end_a = valid[ia] and (ia == last or fb[l])
+            nxt = W[ib + 1] if ib + 1 < 64 else False
+            end_b = valid[ib] and (ib == last or nxt)
+            for (q, is_end, tot) in ((ia, end_a, tot_a), (ib, end_b, tot_b)):
+                if not is_end:
+                    continue
+                if q == last and run_continues and not last_step:
+                    continue
+                head_run = in_head and cum[q] == 0
+                if head_run:
+                    side[2 * c] = tot
+                elif q == last and last_step and tail_cont:
+                    side[2 * c + 1] = tot
+                else:
+                    partial[poff[j] + row_before + cum[q]] = np.float32(tot)
+        carry = inclD[31] if (run_continues and not last_step) else 0.0
+        if W.any():
             in_head = False
-        row_before += int(flags.sum())
+        row_before += int(W.sum())
 
 
 def fixup(fix, chunks, tail_slot, side, partial):
