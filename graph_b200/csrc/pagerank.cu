@@ -45,8 +45,7 @@ namespace gb {
 
 constexpr int PR_WARPS = 32;        // warps per CTA of the sweep kernels: one persistent CTA per SM
 constexpr int PR_THREADS = PR_WARPS * 32;
-constexpr int PR_HOT = 32 * 1024;   // out_scores entries mirrored in shared memory by the SELL kernel
-constexpr int PR_HOT_MAX = 52 * 1024;
+constexpr int PR_SELL_THREADS = 512; // SELL kernel: two 16-warp CTAs per SM and no shared memory (L1 keeps it all)
 constexpr int PR_FIN_THREADS = 256;
 constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;  // sweeps bracketed by CUDA events when profiling is on
 constexpr uint32_t CB_G = 4;                 // block-local ids per group (one 64-bit load per lane)
@@ -54,6 +53,8 @@ constexpr uint32_t CB_BLOCK_DEFAULT = 32768; // source-vector entries per block 
 constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
 constexpr double CB_TAU_DEFAULT = 3.0;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
+constexpr uint32_t CB_LOAD_COST = 4096;      // groups a CTA streams in the time it loads one block (load balancing)
+constexpr uint32_t FIN_WARP_BLOCKS = 256;    // finish: rows with segments in more blocks get a warp each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
 // chunk flags (bits 24.. of PrChunk.w)
 constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
@@ -89,7 +90,7 @@ struct PrPlan {
   uint32_t B = 0, KB = 0;       // block entries, hot blocks
   uint64_t S = 0;               // staircase size = sum of nrows[j]
   uint64_t NG = 0;              // groups in all block streams
-  uint32_t chunk_groups = 0, n_chunks = 0, n_tasks = 0, n_fix = 0;
+  uint32_t chunk_groups = 0, n_chunks = 0, n_fix = 0;
   DevBuf<uint32_t> blk;         // [KB] source block of hot rank j
   DevBuf<uint32_t> nrows;       // [KB] local rows [0, nrows[j]) have a segment in block j (non-increasing)
   DevBuf<uint32_t> poff;        // [KB+1] staircase offsets
@@ -100,8 +101,8 @@ struct PrPlan {
   DevBuf<uint32_t> tail_slot;   // [n_chunks] staircase slot of the segment cut by the chunk end
   DevBuf<double> side;          // [2 n_chunks] head / tail parts of segments cut by chunk boundaries
   DevBuf<uint32_t> fix_list;    // [n_fix] chunks whose tail segment continues in later chunks
-  DevBuf<uint2> tasks;          // [n_tasks] chunk ranges of one block each
-  DevBuf<uint32_t> task_ctr;    // dynamic task counter
+  DevBuf<uint32_t> cfirst;      // [KB+1] first chunk of each block's stream
+  DevBuf<uint2> cta_range;      // [grid_cb] chunks [x, y) of every persistent CTA (balanced by groups + block loads)
   DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
   // SELL-32 (all local active rows; rows < n_cb hold only the edges outside their segments)
   uint32_t num_slices = 0;
@@ -119,13 +120,12 @@ struct PrPlan {
   DevBuf<double> block_err;  // per CTA error partials (SELL CTAs, then finish CTAs)
   DevBuf<double> err_hist;   // error of each sweep of the current batch
   DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
-  uint32_t hot_count = 0;    // entries of out_scores mirrored in shared memory by the SELL kernel
-  size_t smem_sell = 0, smem_cb = 0;
+  size_t smem_cb = 0;
   std::vector<cudaEvent_t> prof_events;
   uint64_t bytes() const {
     return new_id.bytes() + outdeg.bytes() + blk.bytes() + nrows.bytes() + poff.bytes() + cb_ids.bytes() +
            cb_bits.bytes() + partial.bytes() + chunks.bytes() + tail_slot.bytes() + side.bytes() +
-           fix_list.bytes() + tasks.bytes() + rem.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
+           fix_list.bytes() + cfirst.bytes() + cta_range.bytes() + rem.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
            x[1].bytes() + scores.bytes() + block_err.bytes() + err_hist.bytes();
   }
 };
@@ -219,9 +219,11 @@ __global__ void k_blk_edges(const uint32_t* __restrict__ outdeg, uint32_t n, uin
     blk_edges[b] = t;
   }
 }
-// rows_ge[b] = number of (global) rows with in-degree >= dmin[b]; indeg is non-increasing
-__global__ void k_rows_ge(const uint32_t* __restrict__ indeg, uint32_t n_active, const uint32_t* __restrict__ dmin,
-                          uint32_t nblk, uint32_t* __restrict__ rows_ge) {
+// rows_ge[b] = number of (global) rows with in-degree >= dmin[b] (indeg is non-increasing);
+// edges_ge[b] = the in-edges of those rows (deg_prefix = inclusive prefix sums of indeg)
+__global__ void k_rows_ge(const uint32_t* __restrict__ indeg, const unsigned long long* __restrict__ deg_prefix,
+                          uint32_t n_active, const uint32_t* __restrict__ dmin, uint32_t nblk,
+                          uint32_t* __restrict__ rows_ge, unsigned long long* __restrict__ edges_ge) {
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x) {
     const uint32_t d = dmin[b];
     uint32_t lo = 0, hi = n_active;  // first index with indeg < d
@@ -231,8 +233,12 @@ __global__ void k_rows_ge(const uint32_t* __restrict__ indeg, uint32_t n_active,
       else hi = mid;
     }
     rows_ge[b] = lo;
+    edges_ge[b] = lo ? deg_prefix[lo - 1] : 0ull;
   }
 }
+struct U32ToU64 {
+  __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
 
 // One warp per local row that owns segments: classify its in-edges.  An edge from source s (internal
 // id) lands in block s / B; if that block is hot (rank j) and the row is inside the block's row prefix
@@ -462,7 +468,6 @@ struct PrArgs {
   float* peer_next[7];  // peer-mapped copies of x_next (fused allgather over NVLink); n_peers used
   uint32_t n_peers;
   uint32_t n;
-  uint32_t hot_count;   // entries of x_cur mirrored in shared memory by the SELL kernel (multiple of 4)
   float* scores;
   PrDeal deal;
   uint32_t n_loc, n_cb;
@@ -476,13 +481,13 @@ struct PrArgs {
   const uint32_t* cb_bits;
   float* partial;
   const uint4* chunks;
+  uint32_t n_chunks;
   const uint32_t* tail_slot;
   double* side;
   const uint32_t* fix_list;
   uint32_t n_fix;
-  const uint2* tasks;
-  uint32_t n_tasks;
-  uint32_t* task_ctr;
+  const uint32_t* cfirst;
+  const uint2* cta_range;
   float* rem;
   // SELL rows
   const uint4* sell;
@@ -500,53 +505,22 @@ struct PrArgs {
   uint32_t sweep_no;  // 1-based global sweep number
 };
 
-// 8 gathers per lane in straight-line predicated code: ids below hot_n read the shared-memory mirror,
-// all others (except the padding id ~0) read global memory through L1 (ld.global.nc).  Measured
+// 8 gathers per lane in straight-line predicated code (padding id ~0 reads nothing).  Measured in round 1
 // (profiles/r01_sweep_hot_head.txt): per-target if/else made every load wait for a scoreboard slot of
-// the previous one; and every pending miss holds an L1 line, so the hot head must leave L1 room —
-// at 208 KB of shared memory (16 KB of L1) the sweep ran 2.8x slower than at 128 KB (96 KB of L1);
-// ld.global.nc.L1::no_allocate was slower still at every size.
-template <bool HOT>
-__device__ __forceinline__ void pr_gather(const float* x, uint32_t hot_saddr, uint32_t hot_n,
-                                          const uint4& ta, const uint4& tb, float (&v)[8]) {
+// the previous one, and every pending miss holds an L1 line — so this kernel uses NO shared memory at
+// all and leaves the whole 228 KB to L1 (a 128 KB shared-memory mirror of the hottest sources was
+// slower than two mirror-less CTAs per SM: profiles/r02_sweep_breakdown.txt).
+__device__ __forceinline__ void pr_gather(const float* x, const uint4& ta, const uint4& tb, float (&v)[8]) {
   const uint32_t t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-  float vs[8], vg[8];
-  if (HOT) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.lt.u32 p, %1, %2;\n\t"
-          "mov.f32 %0, 0f00000000;\n\t"
-          "@p ld.shared.f32 %0, [%3];\n\t}"
-          : "=f"(vs[j])
-          : "r"(t[j]), "r"(hot_n), "r"(hot_saddr + 4u * t[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.ge.u32 p, %1, %2;\n\t"
-          "setp.ne.and.u32 p, %1, 0xffffffff, p;\n\t"
-          "mov.f32 %0, 0f00000000;\n\t"
-          "@p ld.global.nc.f32 %0, [%3];\n\t}"
-          : "=f"(vg[j])
-          : "r"(t[j]), "r"(hot_n), "l"(x + t[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = vs[j] + vg[j];
-  } else {
-    // no shared-memory mirror (the SELL kernel shares its SM with the column-block kernel)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.ne.u32 p, %1, 0xffffffff;\n\t"
-          "mov.f32 %0, 0f00000000;\n\t"
-          "@p ld.global.nc.f32 %0, [%2];\n\t}"
-          : "=f"(v[j])
-          : "r"(t[j]), "l"(x + t[j]));
-    }
+  for (int j = 0; j < 8; ++j) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.global.nc.f32 %0, [%2];\n\t}"
+        : "=f"(v[j])
+        : "r"(t[j]), "l"(x + t[j]));
   }
 }
 __device__ __forceinline__ float pr_sum8(const float (&v)[8]) {
@@ -669,39 +643,35 @@ template <int NT>
 __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
-  __shared__ uint32_t s_task;
   if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t B = a.B;
   const uint32_t pad2 = B | (B << 16);
-  uint32_t cur_j = CB_NONE;
-  for (;;) {
-    if (threadIdx.x == 0) s_task = atomicAdd(a.task_ctr, 1u);
-    __syncthreads();
-    const uint32_t t = s_task;
-    __syncthreads();
-    if (t >= a.n_tasks) break;
-    const uint2 task = a.tasks[t];
-    const uint32_t j = a.chunks[task.x].w & 0xFFFFFFu;
-    if (j != cur_j) {
-      const uint64_t x0 = (uint64_t)a.blk[j] * B;
-      const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
-      for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x0 + i + 3 < a.n) {
-          v = __ldg(src + i / 4);
-        } else {
-          if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
-          if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
-          if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
-        }
-        *reinterpret_cast<float4*>(xs + i) = v;
+  // this CTA's chunks: a contiguous range of the chunk list (plan-time balance of groups + block loads),
+  // walked one block run at a time
+  const uint2 range = a.cta_range[blockIdx.x];
+  uint32_t c = range.x;
+  while (c < range.y) {
+    const uint32_t j = a.chunks[c].w & 0xFFFFFFu;
+    const uint32_t run_end = min(range.y, __ldg(a.cfirst + j + 1));
+    __syncthreads();  // every warp is done with the previous block
+    const uint64_t x0 = (uint64_t)a.blk[j] * B;
+    const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
+    for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x0 + i + 3 < a.n) {
+        v = __ldg(src + i / 4);
+      } else {
+        if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
+        if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
+        if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
       }
-      if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
-      cur_j = j;
-      __syncthreads();
+      *reinterpret_cast<float4*>(xs + i) = v;
     }
-    for (uint32_t c = task.x + warp; c < task.y; c += NT / 32) cb_chunk(a, xs, c, lane, pad2);
+    if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
+    __syncthreads();
+    for (uint32_t k = c + warp; k < run_end; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
+    c = run_end;
   }
 }
 __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb_body<PR_THREADS>(a); }
@@ -709,19 +679,27 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb
 // fits beside it on the SM
 __global__ void __maxnreg__(56) k_pr_cb_half(const PrArgs a) { pr_cb_body<PR_THREADS / 2>(a); }
 
-// segments cut by chunk boundaries: their parts are added in a fixed order (tiny; after k_pr_cb)
+// Segments cut by chunk boundaries (segments longer than a chunk): one warp per segment adds its parts
+// in a fixed order — the head part of the first chunk, then lanes over the following chunks (a fixed
+// xor tree per batch of 32).  Tiny; runs after k_pr_cb.
 __global__ void k_pr_fixup(const PrArgs a) {
   if (a.ctrl[0] != 0) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_fix; i += gridDim.x * blockDim.x) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = gw; i < a.n_fix; i += nw) {
     const uint32_t c0 = a.fix_list[i];
     double t = a.side[2 * (size_t)c0 + 1];
-    uint32_t k = c0 + 1;
-    for (;; ++k) {
-      const uint32_t fl = a.chunks[k].w >> 24;
-      t += a.side[2 * (size_t)k];
-      if (!((fl & CB_INTERIOR) && (fl & CB_TAIL_CONT))) break;
+    for (uint32_t k0 = c0 + 1;; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      // the walk ends at the first chunk that is not entirely inside the segment (sentinel chunk after the last)
+      const uint32_t fl = a.chunks[min(k, a.n_chunks)].w >> 24;
+      const bool inside = k < a.n_chunks && (fl & CB_INTERIOR) && (fl & CB_TAIL_CONT);
+      const uint32_t stop = __ballot_sync(0xFFFFFFFFu, !inside);
+      const uint32_t upto = stop ? (uint32_t)__ffs(stop) - 1 : 31u;  // last lane that contributes
+      t += warp_sum(lane <= upto ? a.side[2 * (size_t)k] : 0.0);
+      if (stop) break;
     }
-    a.partial[a.tail_slot[c0]] = (float)t;
+    if (lane == 0) a.partial[a.tail_slot[c0]] = (float)t;
   }
 }
 
@@ -730,27 +708,16 @@ __global__ void k_pr_fixup(const PrArgs a) {
 // lane-minor), gathers, and adds in row order.  The next slice's first targets and row metadata are
 // requested while the current slice is processed.  Rows below n_cb only hold the edges that are not in
 // a column-block segment: their sum goes to rem[] and the finish kernel completes them.
-// HOT: mirror the first hot_count sources in shared memory (used when this kernel has the SM to
-// itself); without it the kernel needs no shared memory and runs beside k_pr_cb on the same SMs —
-// the column blocks are bound by the shared-memory pipe and issue slots, this kernel by the
-// L1TEX->XBAR request port, so the two overlap.
-template <bool PEERS, bool HOT, int NT>
-__global__ void __launch_bounds__(NT, HOT ? 1 : 2048 / NT / 2) k_pr_sell(const PrArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* hot = smem;
+// The kernel needs no shared memory: two 512-thread CTAs per SM when it runs alone, one beside a
+// k_pr_cb_half CTA in dual mode.
+template <bool PEERS>
+__global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) {
+  constexpr int NT = PR_SELL_THREADS;
   constexpr int NW = NT / 32;
   __shared__ double warp_err[NW];
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ x = a.x_cur;
-  const uint32_t hot_n = HOT ? a.hot_count : 0;
-  uint32_t hot_saddr = 0;
-  if (HOT) {
-    for (uint32_t i = threadIdx.x * 4; i < hot_n; i += NT * 4)
-      *reinterpret_cast<float4*>(hot + i) = __ldg(reinterpret_cast<const float4*>(x + i));
-    __syncthreads();
-    hot_saddr = (uint32_t)__cvta_generic_to_shared(hot);
-  }
   double err = 0.0;
   const uint32_t stride = gridDim.x * NW;
   const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -802,7 +769,7 @@ __global__ void __launch_bounds__(NT, HOT ? 1 : 2048 / NT / 2) k_pr_sell(const P
       const uint4 na = (q + 2 < w4) ? pr_ld4(base + (q + 2) * 32) : pad;
       const uint4 nb = (q + 3 < w4) ? pr_ld4(base + (q + 3) * 32) : pad;
       float v[8];
-      pr_gather<HOT>(x, hot_saddr, hot_n, ta, tb, v);
+      pr_gather(x, ta, tb, v);
       acc += pr_sum8(v);
       ta = na;
       tb = nb;
@@ -829,8 +796,8 @@ __global__ void __launch_bounds__(NT, HOT ? 1 : 2048 / NT / 2) k_pr_sell(const P
 }
 
 // ---- finish: rows with segments = partials of their blocks (fixed order, f64) + SELL remainder -----
-// Rows that own segments in more than 32 blocks (the hubs: a prefix) get one warp each, lanes striding
-// over the blocks; all other rows one lane each with at most 32 independent loads.  The last CTA to
+// Rows that own segments in more than FIN_WARP_BLOCKS blocks (the hubs: a prefix) get one warp each,
+// lanes striding over the blocks; all other rows one lane each (coalesced across the warp's 32 rows).  The last CTA to
 // finish reduces all CTA error partials in a fixed order and evaluates the stop rule of
 // page_rank.rs:107 on the device.
 __device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __restrict__ nrows, uint32_t KB, uint32_t l) {
@@ -849,7 +816,6 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   __shared__ bool is_last;
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
   double err = 0.0;
   const uint32_t P = a.deal.P, pp = a.deal.p;
   const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
@@ -879,7 +845,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
       s = (double)a.rem[l];
     }
     const uint32_t kb = fin_blocks_of(a.nrows, a.KB, l0);  // the warp's first row has the most blocks
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t j = 0; j < kb; ++j)
       if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     if (on) err += pr_update<PEERS>(gr, (float)s, old, deg, a);
@@ -1084,11 +1050,22 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     const uint32_t nblk = (uint32_t)(((uint64_t)n + B - 1) / B);
     std::vector<uint32_t> h_hot(nblk, CB_NONE), h_blk, h_nrows, h_poff;
     if (p->n_loc && m) {
-      DevBuf<unsigned long long> blk_edges;
+      DevBuf<unsigned long long> blk_edges, deg_prefix, edges_ge;
       DevBuf<uint32_t> dmin, rows_ge;
       GB_TRY(blk_edges.alloc(nblk));
       GB_TRY(dmin.alloc(nblk));
       GB_TRY(rows_ge.alloc(nblk));
+      GB_TRY(edges_ge.alloc(nblk));
+      GB_TRY(deg_prefix.alloc(std::max<uint32_t>(p->n_active, 1)));
+      {
+        cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(indeg.p, U32ToU64());
+        size_t tb = 0;
+        GB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, it, deg_prefix.p, (int)p->n_active, s));
+        DevBuf<uint8_t> tmp;
+        GB_TRY(tmp.alloc(tb));
+        GB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, deg_prefix.p, (int)p->n_active, s));
+        GB_CUDA(cudaStreamSynchronize(s));
+      }
       k_blk_edges<<<nblk, 256, 0, s>>>(p->outdeg.p, n, B, blk_edges.p);
       std::vector<unsigned long long> h_edges(nblk);
       GB_CUDA(cudaMemcpyAsync(h_edges.data(), blk_edges.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
@@ -1100,13 +1077,23 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
           h_dmin[b] = d >= 4294967295.0 ? 0xFFFFFFFFu : std::max<uint32_t>(1u, (uint32_t)d);
         }
       GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)nblk * 4, cudaMemcpyHostToDevice, s));
-      k_rows_ge<<<grid_for(nblk, 128), 128, 0, s>>>(indeg.p, p->n_active, dmin.p, nblk, rows_ge.p);
+      k_rows_ge<<<grid_for(nblk, 128), 128, 0, s>>>(indeg.p, deg_prefix.p, p->n_active, dmin.p, nblk, rows_ge.p,
+                                                     edges_ge.p);
       std::vector<uint32_t> h_rows(nblk);
+      std::vector<unsigned long long> h_ege(nblk);
       GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
+      // a block is only worth its shared-memory load if its segments are expected to hold enough ids
+      // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers)
+      double min_ids = (double)B / 4.0;
+      if (const char* e = getenv("GB_PR_MIN_BLOCK")) min_ids = atof(e);
       std::vector<uint32_t> order;
-      for (uint32_t b = 0; b < nblk; ++b)
-        if (h_dmin[b] != 0xFFFFFFFFu && deal_count(h_rows[b], deal.P, deal.p) > 0) order.push_back(b);
+      for (uint32_t b = 0; b < nblk; ++b) {
+        if (h_dmin[b] == 0xFFFFFFFFu || deal_count(h_rows[b], deal.P, deal.p) == 0) continue;
+        const double expect = (double)h_ege[b] * ((double)h_edges[b] / (double)m) / (double)deal.P;
+        if (expect >= min_ids) order.push_back(b);
+      }
       std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         return h_rows[x] != h_rows[y] ? h_rows[x] > h_rows[y] : x < y;
       });
@@ -1203,7 +1190,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
           p->sell.p);
       GB_CUDA(cudaGetLastError());
     }
-    // 7. chunks and tasks of the column-block kernel
+    // 7. chunks of the column-block kernel and every persistent CTA's share of them
+    p->grid_cb = 0;
     if (p->NG) {
       // first group of every block's stream
       DevBuf<uint32_t> gbeg;
@@ -1212,27 +1200,36 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<uint32_t> h_gbeg(p->KB + 1);
       GB_CUDA(cudaMemcpyAsync(h_gbeg.data(), gbeg.p, (size_t)(p->KB + 1) * 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      // a task (one block load) should be ~1/8 of an SM's share; 64+ chunks per task keep 32 warps busy
-      uint64_t task_groups = std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 8), 2048);
+      // ~128 chunks per CTA (4 per warp) keep the warps of a CTA level; at most 2048 groups per chunk
       uint32_t C = env_u32("GB_PR_CHUNK", 0);
-      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(((task_groups / 64) + 31) / 32 * 32, 64), 1024);
+      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 128), 64), 2048);
       C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
-      const uint32_t TC = (uint32_t)std::max<uint64_t>(32, (task_groups + C - 1) / C);
       p->chunk_groups = C;
       std::vector<uint32_t> h_cfirst(p->KB + 1, 0);
-      std::vector<uint2> h_tasks;
-      for (uint32_t j = 0; j < p->KB; ++j) {
-        const uint32_t G = h_gbeg[j + 1] - h_gbeg[j];
-        const uint32_t nc = (G + C - 1) / C;
-        h_cfirst[j + 1] = h_cfirst[j] + nc;
-        for (uint32_t c = 0; c < nc; c += TC)
-          h_tasks.push_back(make_uint2(h_cfirst[j] + c, h_cfirst[j] + std::min(nc, c + TC)));
-      }
+      for (uint32_t j = 0; j < p->KB; ++j) h_cfirst[j + 1] = h_cfirst[j] + (h_gbeg[j + 1] - h_gbeg[j] + C - 1) / C;
       p->n_chunks = h_cfirst[p->KB];
-      p->n_tasks = (uint32_t)h_tasks.size();
-      DevBuf<uint32_t> cfirst;
-      GB_TRY(upload(s, &cfirst, h_cfirst));
-      GB_TRY(upload(s, &p->tasks, h_tasks));
+      // contiguous chunk ranges of equal cost: a chunk costs its groups, a block run one block load
+      p->grid_cb = (unsigned)std::min<uint64_t>(p->n_chunks, (uint64_t)dev_sms);  // one persistent CTA per SM
+      {
+        const double total = (double)p->NG + (double)CB_LOAD_COST * p->KB;
+        std::vector<uint2> h_range(p->grid_cb);
+        uint32_t j = 0, c = 0;
+        double acc = 0.0;  // cost of chunks [0, c) (the load of block j is charged with its first chunk)
+        for (unsigned i = 0; i < p->grid_cb; ++i) {
+          const double target = total * (double)(i + 1) / (double)p->grid_cb;
+          const uint32_t begin = c;
+          while (c < p->n_chunks && (acc < target || i + 1 == p->grid_cb)) {
+            while (c >= h_cfirst[j + 1]) ++j;
+            const uint32_t g0 = h_gbeg[j] + (c - h_cfirst[j]) * C;
+            const uint32_t g1 = std::min<uint32_t>(h_gbeg[j + 1], g0 + C);
+            acc += (double)(g1 - g0) + (c == h_cfirst[j] ? (double)CB_LOAD_COST : 0.0);
+            ++c;
+          }
+          h_range[i] = make_uint2(begin, c);
+        }
+        GB_TRY(upload(s, &p->cta_range, h_range));
+      }
+      GB_TRY(upload(s, &p->cfirst, h_cfirst));
       GB_TRY(p->chunks.alloc(p->n_chunks, 1));
       GB_TRY(p->tail_slot.alloc(p->n_chunks));
       GB_TRY(p->fix_list.alloc(p->n_chunks));
@@ -1240,7 +1237,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_CUDA(cudaMemsetAsync(p->side.p, 0, ((size_t)2 * p->n_chunks + 2) * 8, s));
       GB_CUDA(cudaMemsetAsync(p->chunks.p + p->n_chunks, 0, sizeof(uint4), s));  // sentinel: ends every fixup walk
       uint32_t* d_nfix = reinterpret_cast<uint32_t*>(counters.p + 3);
-      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, cfirst.p, p->KB,
+      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, p->cfirst.p, p->KB,
                                                            p->n_chunks, C, p->chunks.p, p->tail_slot.p,
                                                            p->fix_list.p, d_nfix);
       GB_CUDA(cudaGetLastError());
@@ -1251,37 +1248,26 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_TRY(p->tail_slot.alloc(1));
       GB_TRY(p->fix_list.alloc(1));
       GB_TRY(p->side.alloc(2));
-      GB_TRY(p->tasks.alloc(1));
+      GB_TRY(p->cfirst.alloc(1));
+      GB_TRY(p->cta_range.alloc(1));
     }
     GB_TRY(p->partial.alloc(std::max<uint64_t>(p->S, 1)));
     GB_CUDA(cudaMemsetAsync(p->partial.p, 0, std::max<uint64_t>(p->S, 1) * 4, s));
     GB_TRY(p->rem.alloc(std::max<uint32_t>(p->n_cb, 1)));
-    GB_TRY(p->task_ctr.alloc(1));
-    GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
     // 8. launch shapes and error buffers
-    uint32_t hot_cap = PR_HOT;
-    if (const char* e = getenv("GB_PR_HOT")) hot_cap = std::min<uint32_t>((uint32_t)PR_HOT_MAX, (uint32_t)atoi(e)) & ~3u;
-    p->hot_count = std::min<uint32_t>(hot_cap, n & ~3u);
-    p->smem_sell = (size_t)p->hot_count * sizeof(float) + 16;
     p->smem_cb = ((size_t)B + 4) * sizeof(float);
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<false, true, PR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)p->smem_sell));
-    GB_CUDA(cudaFuncSetAttribute(k_pr_sell<true, true, PR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)p->smem_sell));
     // dual mode needs both kernels to have work; GB_PR_DUAL=0 runs them back to back on one stream
-    p->dual = p->n_tasks > 0 && p->num_slices > 0 && env_u32("GB_PR_DUAL", 1) != 0;
+    p->dual = p->grid_cb > 0 && p->num_slices > 0 && env_u32("GB_PR_DUAL", 1) != 0;
     if (p->dual) {
       GB_CUDA(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
       GB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
       GB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     }
-    p->grid_cb = (unsigned)std::min<uint64_t>(p->n_tasks, (uint64_t)dev_sms);  // one persistent CTA per SM
-    const uint32_t sell_warps = p->dual ? PR_WARPS / 2 : PR_WARPS;
-    const uint64_t want_sell = ((uint64_t)p->num_slices + sell_warps - 1) / sell_warps;
-    p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * (p->dual ? 2 : 1));
-    p->n_fin_warp = p->KB > 32 ? std::min<uint32_t>(p->n_cb, (h_nrows[32] + 31) / 32 * 32) : 0;
+    const uint64_t want_sell = ((uint64_t)p->num_slices + PR_SELL_THREADS / 32 - 1) / (PR_SELL_THREADS / 32);
+    p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * 2);
+    p->n_fin_warp = p->KB > FIN_WARP_BLOCKS ? std::min<uint32_t>(p->n_cb, (h_nrows[FIN_WARP_BLOCKS] + 31) / 32 * 32) : 0;
     const uint64_t fin_tasks = (uint64_t)p->n_fin_warp + (p->n_cb - p->n_fin_warp + 31) / 32;
     const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
@@ -1319,13 +1305,13 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.cb_bits = p->cb_bits.p;
   a.partial = p->partial.p;
   a.chunks = p->chunks.p;
+  a.n_chunks = p->n_chunks;
   a.tail_slot = p->tail_slot.p;
   a.side = p->side.p;
   a.fix_list = p->fix_list.p;
   a.n_fix = p->n_fix;
-  a.tasks = p->tasks.p;
-  a.n_tasks = p->n_tasks;
-  a.task_ctr = p->task_ctr.p;
+  a.cfirst = p->cfirst.p;
+  a.cta_range = p->cta_range.p;
   a.rem = p->rem.p;
   a.sell = p->sell.p;
   a.slice_meta = p->slice_meta.p;
@@ -1339,7 +1325,6 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.tolerance = tolerance;
   a.n_peers = 0;
   a.mc_next = nullptr;
-  a.hot_count = p->hot_count;
   return a;
 }
 
@@ -1347,12 +1332,12 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
 // then finish; *launches is advanced by the kernels launched
 template <bool PEERS>
 static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, uint64_t* launches) {
-  const unsigned fix_grid = grid_for(p->n_fix, 128, 64);
+  const unsigned fix_grid = grid_for((uint64_t)p->n_fix * 32, 128, 296);
   if (p->dual) {
     GB_CUDA(cudaEventRecord(p->ev_fork, s));
     GB_CUDA(cudaStreamWaitEvent(p->s2, p->ev_fork, 0));
     k_pr_cb_half<<<p->grid_cb, PR_THREADS / 2, p->smem_cb, s>>>(a);
-    k_pr_sell<PEERS, false, PR_THREADS / 2><<<p->grid_sell, PR_THREADS / 2, 0, p->s2>>>(a);
+    k_pr_sell<PEERS><<<p->grid_sell, PR_SELL_THREADS, 0, p->s2>>>(a);
     if (p->n_fix) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
     GB_CUDA(cudaEventRecord(p->ev_join, p->s2));
     GB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
@@ -1364,7 +1349,7 @@ static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, 
       *launches += 1 + (p->n_fix ? 1 : 0);
     }
     if (p->grid_sell) {
-      k_pr_sell<PEERS, true, PR_THREADS><<<p->grid_sell, PR_THREADS, p->smem_sell, s>>>(a);
+      k_pr_sell<PEERS><<<p->grid_sell, PR_SELL_THREADS, 0, s>>>(a);
       *launches += 1;
     }
   }
@@ -1413,7 +1398,6 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
   k_pr_init<<<grid_for(n, 256), 256, 0, s>>>(n, p->n_active, init, base, p->deal, p->outdeg.p, p->x[0].p, p->x[1].p,
                                             p->scores.p);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
-  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   g->timing.kernel_launches += 1;
 
   PrArgs a = make_args(p, base, cfg->damping_factor, cfg->tolerance);
@@ -1578,7 +1562,6 @@ gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0,
   gb::k_pr_init<<<gb::grid_for(p->n, 256), 256, 0, s>>>(p->n, p->n_active, init, base, p->deal, p->outdeg.p, d_x0,
                                                        d_x1, d_scores);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
-  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }
@@ -1647,7 +1630,7 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
   stats->segments = p->S;
   stats->groups = p->NG;
   stats->chunks = p->n_chunks;
-  stats->tasks = p->n_tasks;
+  stats->tasks = p->grid_cb;
   stats->cut_segments = p->n_fix;
   stats->chunk_groups = p->chunk_groups;
   stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) + (p->grid_cb && p->n_fix ? 1 : 0);
