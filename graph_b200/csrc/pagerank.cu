@@ -104,6 +104,7 @@ struct PrPlan {
   DevBuf<uint32_t> cfirst;      // [KB+1] first chunk of each block's stream
   DevBuf<uint2> cta_range;      // [grid_cb] chunks [x, y) of every persistent CTA (balanced by groups + block loads)
   DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
+  DevBuf<uint32_t> fin_kb;      // [ceil(n_cb / 32)] blocks of the first row of each 32-row group (finish kernel)
   // SELL-32 (all local active rows; rows < n_cb hold only the edges outside their segments)
   uint32_t num_slices = 0;
   DevBuf<uint4> sell;         // slice-major, then 4-edge group, then lane
@@ -125,7 +126,7 @@ struct PrPlan {
   uint64_t bytes() const {
     return new_id.bytes() + outdeg.bytes() + blk.bytes() + nrows.bytes() + poff.bytes() + cb_ids.bytes() +
            cb_bits.bytes() + partial.bytes() + chunks.bytes() + tail_slot.bytes() + side.bytes() +
-           fix_list.bytes() + cfirst.bytes() + cta_range.bytes() + rem.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
+           fix_list.bytes() + cfirst.bytes() + cta_range.bytes() + rem.bytes() + fin_kb.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
            x[1].bytes() + scores.bytes() + block_err.bytes() + err_hist.bytes();
   }
 };
@@ -408,9 +409,11 @@ __global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* _
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
 }
 
-// Chunks: block j's stream [gbeg[j], gbeg[j+1]) is cut every C groups; a cut inside a segment moves to
-// the segment's end unless the segment is longer than C groups, in which case the cut stays and both
-// neighbours handle a PART of it (side buffer + fixup), so no warp ever owns more than 2C groups.
+// Chunks: block j's stream [gbeg[j], gbeg[j+1]) is cut every C_j groups; a cut inside a segment moves to
+// the segment's end unless the segment is longer than C_j groups, in which case the cut stays and both
+// neighbours handle a PART of it (side buffer + fixup), so no warp ever owns more than 2 C_j groups.
+// C_j shrinks for thin blocks so that every block's stream is spread over all warps of a CTA (a lone
+// warp runs at its dependency latency, ~10x below the SM's throughput).
 struct CbCut {
   uint32_t pos, row;
   bool mid;
@@ -431,8 +434,8 @@ __device__ __forceinline__ CbCut cb_cut(const uint32_t* __restrict__ goff_j, uin
 }
 __global__ void k_cb_chunks(const uint32_t* __restrict__ goff, const uint32_t* __restrict__ poff,
                             const uint32_t* __restrict__ nrows, const uint32_t* __restrict__ gbeg,
-                            const uint32_t* __restrict__ cfirst, uint32_t KB, uint32_t n_chunks, uint32_t C,
-                            uint4* __restrict__ chunks, uint32_t* __restrict__ tail_slot,
+                            const uint32_t* __restrict__ cfirst, const uint32_t* __restrict__ cgrp, uint32_t KB,
+                            uint32_t n_chunks, uint4* __restrict__ chunks, uint32_t* __restrict__ tail_slot,
                             uint32_t* __restrict__ fix_list, uint32_t* __restrict__ n_fix) {
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = KB;  // block with cfirst[j] <= c < cfirst[j + 1]
@@ -442,6 +445,7 @@ __global__ void k_cb_chunks(const uint32_t* __restrict__ goff, const uint32_t* _
       else hi = mid;
     }
     const uint32_t j = lo, k = c - cfirst[j];
+    const uint32_t C = cgrp[j];  // groups per chunk in this block (thin blocks use small chunks)
     const uint32_t* goff_j = goff + poff[j];
     const uint32_t nr = nrows[j], g0 = gbeg[j], g1 = gbeg[j + 1];
     const bool last = c + 1 == cfirst[j + 1];
@@ -471,7 +475,8 @@ struct PrArgs {
   float* scores;
   PrDeal deal;
   uint32_t n_loc, n_cb;
-  uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in more than 32 blocks (finish: one warp each)
+  uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in many blocks (finish: one warp each)
+  const uint32_t* fin_kb;  // [ceil(n_cb / 32)] blocks in which the first row of each 32-row group owns a segment
   // column blocks
   uint32_t B, KB;
   const uint32_t* blk;
@@ -800,11 +805,11 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
 // lanes striding over the blocks; all other rows one lane each (coalesced across the warp's 32 rows).  The last CTA to
 // finish reduces all CTA error partials in a fixed order and evaluates the stop rule of
 // page_rank.rs:107 on the device.
-__device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __restrict__ nrows, uint32_t KB, uint32_t l) {
+__host__ __device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __restrict__ nrows, uint32_t KB, uint32_t l) {
   uint32_t lo = 0, hi = KB;  // first j with nrows[j] <= l  (nrows is non-increasing)
   while (lo < hi) {
     const uint32_t mid = (lo + hi) / 2;
-    if (__ldg(nrows + mid) > l) lo = mid + 1;
+    if (nrows[mid] > l) lo = mid + 1;
     else hi = mid;
   }
   return lo;
@@ -821,9 +826,10 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
   // hub rows: one warp per row
   for (uint32_t l = gw; l < a.n_fin_warp; l += nw) {
-    const uint32_t kb = fin_blocks_of(a.nrows, a.KB, l);
+    const uint32_t kb = __ldg(a.fin_kb + (l >> 5));  // blocks of the first row of l's 32-row group (>= l's)
     double s = 0.0;
-    for (uint32_t j = lane; j < kb; j += 32) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
+    for (uint32_t j = lane; j < kb; j += 32)
+      if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     s = warp_sum(s);
     if (lane == 0) {
       const uint32_t gr = deal_global(l, P, pp);
@@ -844,7 +850,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
       deg = a.outdeg[gr];
       s = (double)a.rem[l];
     }
-    const uint32_t kb = fin_blocks_of(a.nrows, a.KB, l0);  // the warp's first row has the most blocks
+    const uint32_t kb = __ldg(a.fin_kb + (l0 >> 5));  // blocks of the warp's first row (it has the most)
 #pragma unroll 8
     for (uint32_t j = 0; j < kb; ++j)
       if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
@@ -1084,9 +1090,11 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      // a block is only worth its shared-memory load if its segments are expected to hold enough ids
-      // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers)
-      double min_ids = (double)B / 4.0;
+      // GB_PR_MIN_BLOCK (experiment): drop blocks whose segments are expected to hold fewer ids than this
+      // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers).
+      // Default 0: a thin block costs one 128 KB load (~2 us on one SM), while its ids would otherwise
+      // lengthen the SELL lanes of the hub rows, which one lane walks serially.
+      double min_ids = 0.0;
       if (const char* e = getenv("GB_PR_MIN_BLOCK")) min_ids = atof(e);
       std::vector<uint32_t> order;
       for (uint32_t b = 0; b < nblk; ++b) {
@@ -1200,13 +1208,18 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<uint32_t> h_gbeg(p->KB + 1);
       GB_CUDA(cudaMemcpyAsync(h_gbeg.data(), gbeg.p, (size_t)(p->KB + 1) * 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      // ~128 chunks per CTA (4 per warp) keep the warps of a CTA level; at most 2048 groups per chunk
+      // ~128 chunks per CTA (4 per warp) keep the warps of a CTA level; at most 2048 groups per chunk;
+      // a thin block is cut into >= 64 chunks (down to one 64-group step each)
       uint32_t C = env_u32("GB_PR_CHUNK", 0);
       if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 128), 64), 2048);
       C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
       p->chunk_groups = C;
-      std::vector<uint32_t> h_cfirst(p->KB + 1, 0);
-      for (uint32_t j = 0; j < p->KB; ++j) h_cfirst[j + 1] = h_cfirst[j] + (h_gbeg[j + 1] - h_gbeg[j] + C - 1) / C;
+      std::vector<uint32_t> h_cfirst(p->KB + 1, 0), h_cgrp(p->KB, C);
+      for (uint32_t j = 0; j < p->KB; ++j) {
+        const uint32_t G = h_gbeg[j + 1] - h_gbeg[j];
+        h_cgrp[j] = std::min<uint32_t>(C, std::max<uint32_t>(std::min<uint32_t>(64u, C), (G / 64 + 63) / 64 * 64));
+        h_cfirst[j + 1] = h_cfirst[j] + (G + h_cgrp[j] - 1) / h_cgrp[j];
+      }
       p->n_chunks = h_cfirst[p->KB];
       // contiguous chunk ranges of equal cost: a chunk costs its groups, a block run one block load
       p->grid_cb = (unsigned)std::min<uint64_t>(p->n_chunks, (uint64_t)dev_sms);  // one persistent CTA per SM
@@ -1220,8 +1233,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
           const uint32_t begin = c;
           while (c < p->n_chunks && (acc < target || i + 1 == p->grid_cb)) {
             while (c >= h_cfirst[j + 1]) ++j;
-            const uint32_t g0 = h_gbeg[j] + (c - h_cfirst[j]) * C;
-            const uint32_t g1 = std::min<uint32_t>(h_gbeg[j + 1], g0 + C);
+            const uint32_t g0 = h_gbeg[j] + (c - h_cfirst[j]) * h_cgrp[j];
+            const uint32_t g1 = std::min<uint32_t>(h_gbeg[j + 1], g0 + h_cgrp[j]);
             acc += (double)(g1 - g0) + (c == h_cfirst[j] ? (double)CB_LOAD_COST : 0.0);
             ++c;
           }
@@ -1230,6 +1243,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
         GB_TRY(upload(s, &p->cta_range, h_range));
       }
       GB_TRY(upload(s, &p->cfirst, h_cfirst));
+      DevBuf<uint32_t> cgrp;
+      GB_TRY(upload(s, &cgrp, h_cgrp));
       GB_TRY(p->chunks.alloc(p->n_chunks, 1));
       GB_TRY(p->tail_slot.alloc(p->n_chunks));
       GB_TRY(p->fix_list.alloc(p->n_chunks));
@@ -1237,8 +1252,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_CUDA(cudaMemsetAsync(p->side.p, 0, ((size_t)2 * p->n_chunks + 2) * 8, s));
       GB_CUDA(cudaMemsetAsync(p->chunks.p + p->n_chunks, 0, sizeof(uint4), s));  // sentinel: ends every fixup walk
       uint32_t* d_nfix = reinterpret_cast<uint32_t*>(counters.p + 3);
-      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, p->cfirst.p, p->KB,
-                                                           p->n_chunks, C, p->chunks.p, p->tail_slot.p,
+      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, p->cfirst.p, cgrp.p,
+                                                           p->KB, p->n_chunks, p->chunks.p, p->tail_slot.p,
                                                            p->fix_list.p, d_nfix);
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaMemcpyAsync(&p->n_fix, d_nfix, 4, cudaMemcpyDeviceToHost, s));
@@ -1254,6 +1269,11 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     GB_TRY(p->partial.alloc(std::max<uint64_t>(p->S, 1)));
     GB_CUDA(cudaMemsetAsync(p->partial.p, 0, std::max<uint64_t>(p->S, 1) * 4, s));
     GB_TRY(p->rem.alloc(std::max<uint32_t>(p->n_cb, 1)));
+    {
+      std::vector<uint32_t> h_kb((p->n_cb + 31) / 32);
+      for (size_t w = 0; w < h_kb.size(); ++w) h_kb[w] = fin_blocks_of(h_nrows.data(), p->KB, (uint32_t)w * 32);
+      GB_TRY(upload(s, &p->fin_kb, h_kb));
+    }
     // 8. launch shapes and error buffers
     p->smem_cb = ((size_t)B + 4) * sizeof(float);
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
@@ -1313,6 +1333,7 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.cfirst = p->cfirst.p;
   a.cta_range = p->cta_range.p;
   a.rem = p->rem.p;
+  a.fin_kb = p->fin_kb.p;
   a.sell = p->sell.p;
   a.slice_meta = p->slice_meta.p;
   a.num_slices = p->num_slices;
