@@ -53,8 +53,8 @@ constexpr uint32_t CB_BLOCK_DEFAULT = 32768; // source-vector entries per block 
 constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
 constexpr double CB_TAU_DEFAULT = 3.0;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
-constexpr uint32_t CB_LOAD_COST = 4096;      // groups a CTA streams in the time it loads one block (load balancing)
-constexpr uint32_t FIN_WARP_BLOCKS = 256;    // finish: rows with segments in more blocks get a warp each
+constexpr uint32_t CB_TASK_CHUNKS = 64;      // chunks per task (two per warp)
+constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
 // chunk flags (bits 24.. of PrChunk.w)
 constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
@@ -90,7 +90,7 @@ struct PrPlan {
   uint32_t B = 0, KB = 0;       // block entries, hot blocks
   uint64_t S = 0;               // staircase size = sum of nrows[j]
   uint64_t NG = 0;              // groups in all block streams
-  uint32_t chunk_groups = 0, n_chunks = 0, n_fix = 0;
+  uint32_t chunk_groups = 0, n_chunks = 0, n_tasks = 0, n_fix = 0;
   DevBuf<uint32_t> blk;         // [KB] source block of hot rank j
   DevBuf<uint32_t> nrows;       // [KB] local rows [0, nrows[j]) have a segment in block j (non-increasing)
   DevBuf<uint32_t> poff;        // [KB+1] staircase offsets
@@ -101,8 +101,8 @@ struct PrPlan {
   DevBuf<uint32_t> tail_slot;   // [n_chunks] staircase slot of the segment cut by the chunk end
   DevBuf<double> side;          // [2 n_chunks] head / tail parts of segments cut by chunk boundaries
   DevBuf<uint32_t> fix_list;    // [n_fix] chunks whose tail segment continues in later chunks
-  DevBuf<uint32_t> cfirst;      // [KB+1] first chunk of each block's stream
-  DevBuf<uint2> cta_range;      // [grid_cb] chunks [x, y) of every persistent CTA (balanced by groups + block loads)
+  DevBuf<uint2> tasks;          // [n_tasks] chunk ranges of one block each, fattest blocks first
+  DevBuf<uint32_t> task_ctr;    // dynamic task counter (reset by the finish kernel)
   DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
   DevBuf<uint32_t> fin_kb;      // [ceil(n_cb / 32)] blocks of the first row of each 32-row group (finish kernel)
   // SELL-32 (all local active rows; rows < n_cb hold only the edges outside their segments)
@@ -126,7 +126,7 @@ struct PrPlan {
   uint64_t bytes() const {
     return new_id.bytes() + outdeg.bytes() + blk.bytes() + nrows.bytes() + poff.bytes() + cb_ids.bytes() +
            cb_bits.bytes() + partial.bytes() + chunks.bytes() + tail_slot.bytes() + side.bytes() +
-           fix_list.bytes() + cfirst.bytes() + cta_range.bytes() + rem.bytes() + fin_kb.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
+           fix_list.bytes() + tasks.bytes() + rem.bytes() + fin_kb.bytes() + sell.bytes() + slice_meta.bytes() + x[0].bytes() +
            x[1].bytes() + scores.bytes() + block_err.bytes() + err_hist.bytes();
   }
 };
@@ -475,7 +475,7 @@ struct PrArgs {
   float* scores;
   PrDeal deal;
   uint32_t n_loc, n_cb;
-  uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in many blocks (finish: one warp each)
+  uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in many blocks (finish: one CTA per 32 rows)
   const uint32_t* fin_kb;  // [ceil(n_cb / 32)] blocks in which the first row of each 32-row group owns a segment
   // column blocks
   uint32_t B, KB;
@@ -491,8 +491,9 @@ struct PrArgs {
   double* side;
   const uint32_t* fix_list;
   uint32_t n_fix;
-  const uint32_t* cfirst;
-  const uint2* cta_range;
+  const uint2* tasks;
+  uint32_t n_tasks;
+  uint32_t* task_ctr;
   float* rem;
   // SELL rows
   const uint4* sell;
@@ -644,39 +645,46 @@ __device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint3
   else cb_chunk_impl<false>(a, xs, c, ch, lane, pad2);
 }
 
+// Persistent CTAs pull TASKS (up to 64 consecutive chunks of one block) from an atomic counter, fattest
+// blocks first: self-balancing whatever else shares the SM (the SELL kernel in dual mode) and however
+// wrong a cost model of the thin blocks would be (a static split ran 2.4x slower: profiles/r02_*).
 template <int NT>
 __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
+  __shared__ uint32_t s_task;
   if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t B = a.B;
   const uint32_t pad2 = B | (B << 16);
-  // this CTA's chunks: a contiguous range of the chunk list (plan-time balance of groups + block loads),
-  // walked one block run at a time
-  const uint2 range = a.cta_range[blockIdx.x];
-  uint32_t c = range.x;
-  while (c < range.y) {
-    const uint32_t j = a.chunks[c].w & 0xFFFFFFu;
-    const uint32_t run_end = min(range.y, __ldg(a.cfirst + j + 1));
-    __syncthreads();  // every warp is done with the previous block
-    const uint64_t x0 = (uint64_t)a.blk[j] * B;
-    const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
-    for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (x0 + i + 3 < a.n) {
-        v = __ldg(src + i / 4);
-      } else {
-        if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
-        if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
-        if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
-      }
-      *reinterpret_cast<float4*>(xs + i) = v;
-    }
-    if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
+  uint32_t cur_j = CB_NONE;
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(a.task_ctr, 1u);
+    __syncthreads();  // also: every warp is done with the previous task's block
+    const uint32_t t = s_task;
     __syncthreads();
-    for (uint32_t k = c + warp; k < run_end; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
-    c = run_end;
+    if (t >= a.n_tasks) break;
+    const uint2 task = a.tasks[t];
+    const uint32_t j = a.chunks[task.x].w & 0xFFFFFFu;
+    if (j != cur_j) {
+      const uint64_t x0 = (uint64_t)a.blk[j] * B;
+      const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
+      for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x0 + i + 3 < a.n) {
+          v = __ldg(src + i / 4);
+        } else {
+          if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
+          if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
+          if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
+        }
+        *reinterpret_cast<float4*>(xs + i) = v;
+      }
+      if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
+      cur_j = j;
+      __syncthreads();
+    }
+    for (uint32_t k = task.x + warp; k < task.y; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
   }
 }
 __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb_body<PR_THREADS>(a); }
@@ -801,8 +809,8 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
 }
 
 // ---- finish: rows with segments = partials of their blocks (fixed order, f64) + SELL remainder -----
-// Rows that own segments in more than FIN_WARP_BLOCKS blocks (the hubs: a prefix) get one warp each,
-// lanes striding over the blocks; all other rows one lane each (coalesced across the warp's 32 rows).  The last CTA to
+// 32-row groups that own segments in more than FIN_CTA_BLOCKS blocks (the hubs: a prefix) get a CTA
+// each; all other rows one lane each (coalesced across the warp's 32 rows).  The last CTA to
 // finish reduces all CTA error partials in a fixed order and evaluates the stop rule of
 // page_rank.rs:107 on the device.
 __host__ __device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __restrict__ nrows, uint32_t KB, uint32_t l) {
@@ -823,20 +831,30 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double err = 0.0;
   const uint32_t P = a.deal.P, pp = a.deal.p;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
   const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
-  // hub rows: one warp per row
-  for (uint32_t l = gw; l < a.n_fin_warp; l += nw) {
-    const uint32_t kb = __ldg(a.fin_kb + (l >> 5));  // blocks of the first row of l's 32-row group (>= l's)
+  // hub rows (segments in more than FIN_CTA_BLOCKS blocks): one CTA per 32-row group — lane = row,
+  // warp w adds blocks w, w + 8, ... (independent coalesced loads), warp 0 adds the 8 sums in order
+  __shared__ double part[FIN_WARPS][32];
+  for (uint32_t g = blockIdx.x; g * 32 < a.n_fin_warp; g += gridDim.x) {
+    const uint32_t l = g * 32 + lane;
+    const uint32_t kb = __ldg(a.fin_kb + g);  // blocks of the group's first row (it has the most)
     double s = 0.0;
-    for (uint32_t j = lane; j < kb; j += 32)
+#pragma unroll 4
+    for (uint32_t j = warp; j < kb; j += FIN_WARPS)
       if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
-    s = warp_sum(s);
-    if (lane == 0) {
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && l < a.n_cb) {
+      double t = (double)a.rem[l];
+#pragma unroll
+      for (int w = 0; w < FIN_WARPS; ++w) t += part[w][lane];
       const uint32_t gr = deal_global(l, P, pp);
-      err += pr_update<PEERS>(gr, (float)(s + (double)a.rem[l]), a.scores[gr], a.outdeg[gr], a);
+      err += pr_update<PEERS>(gr, (float)t, a.scores[gr], a.outdeg[gr], a);
     }
+    __syncthreads();
   }
-  // all other rows with segments: one lane per row, at most 32 blocks each
+  // all other rows with segments: one lane per row
   const uint32_t tail_warps = (a.n_cb - a.n_fin_warp + 31) / 32;
   for (uint32_t w = gw; w < tail_warps; w += nw) {
     const uint32_t l0 = a.n_fin_warp + 32 * w, l = l0 + lane;
@@ -1208,42 +1226,29 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<uint32_t> h_gbeg(p->KB + 1);
       GB_CUDA(cudaMemcpyAsync(h_gbeg.data(), gbeg.p, (size_t)(p->KB + 1) * 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      // ~128 chunks per CTA (4 per warp) keep the warps of a CTA level; at most 2048 groups per chunk;
-      // a thin block is cut into >= 64 chunks (down to one 64-group step each)
+      // ~10 tasks per SM keep the dynamic schedule level; a task is 64 chunks (two per warp) of at most
+      // 2048 groups; a thin block is cut into >= 64 chunks (down to one 64-group step each) so that all
+      // warps share it — a lone warp runs at its dependency latency, ~10x below the SM's throughput
       uint32_t C = env_u32("GB_PR_CHUNK", 0);
-      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 128), 64), 2048);
+      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 10 * CB_TASK_CHUNKS), 64), 2048);
       C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
       p->chunk_groups = C;
       std::vector<uint32_t> h_cfirst(p->KB + 1, 0), h_cgrp(p->KB, C);
+      std::vector<uint2> h_tasks;
       for (uint32_t j = 0; j < p->KB; ++j) {
         const uint32_t G = h_gbeg[j + 1] - h_gbeg[j];
         h_cgrp[j] = std::min<uint32_t>(C, std::max<uint32_t>(std::min<uint32_t>(64u, C), (G / 64 + 63) / 64 * 64));
-        h_cfirst[j + 1] = h_cfirst[j] + (G + h_cgrp[j] - 1) / h_cgrp[j];
+        const uint32_t nc = (G + h_cgrp[j] - 1) / h_cgrp[j];
+        h_cfirst[j + 1] = h_cfirst[j] + nc;
+        for (uint32_t c = 0; c < nc; c += CB_TASK_CHUNKS)
+          h_tasks.push_back(make_uint2(h_cfirst[j] + c, h_cfirst[j] + std::min(nc, c + CB_TASK_CHUNKS)));
       }
       p->n_chunks = h_cfirst[p->KB];
-      // contiguous chunk ranges of equal cost: a chunk costs its groups, a block run one block load
-      p->grid_cb = (unsigned)std::min<uint64_t>(p->n_chunks, (uint64_t)dev_sms);  // one persistent CTA per SM
-      {
-        const double total = (double)p->NG + (double)CB_LOAD_COST * p->KB;
-        std::vector<uint2> h_range(p->grid_cb);
-        uint32_t j = 0, c = 0;
-        double acc = 0.0;  // cost of chunks [0, c) (the load of block j is charged with its first chunk)
-        for (unsigned i = 0; i < p->grid_cb; ++i) {
-          const double target = total * (double)(i + 1) / (double)p->grid_cb;
-          const uint32_t begin = c;
-          while (c < p->n_chunks && (acc < target || i + 1 == p->grid_cb)) {
-            while (c >= h_cfirst[j + 1]) ++j;
-            const uint32_t g0 = h_gbeg[j] + (c - h_cfirst[j]) * h_cgrp[j];
-            const uint32_t g1 = std::min<uint32_t>(h_gbeg[j + 1], g0 + h_cgrp[j]);
-            acc += (double)(g1 - g0) + (c == h_cfirst[j] ? (double)CB_LOAD_COST : 0.0);
-            ++c;
-          }
-          h_range[i] = make_uint2(begin, c);
-        }
-        GB_TRY(upload(s, &p->cta_range, h_range));
-      }
-      GB_TRY(upload(s, &p->cfirst, h_cfirst));
-      DevBuf<uint32_t> cgrp;
+      p->n_tasks = (uint32_t)h_tasks.size();
+      p->grid_cb = (unsigned)std::min<uint64_t>(p->n_tasks, (uint64_t)dev_sms);  // one persistent CTA per SM
+      GB_TRY(upload(s, &p->tasks, h_tasks));
+      DevBuf<uint32_t> cfirst, cgrp;
+      GB_TRY(upload(s, &cfirst, h_cfirst));
       GB_TRY(upload(s, &cgrp, h_cgrp));
       GB_TRY(p->chunks.alloc(p->n_chunks, 1));
       GB_TRY(p->tail_slot.alloc(p->n_chunks));
@@ -1252,7 +1257,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_CUDA(cudaMemsetAsync(p->side.p, 0, ((size_t)2 * p->n_chunks + 2) * 8, s));
       GB_CUDA(cudaMemsetAsync(p->chunks.p + p->n_chunks, 0, sizeof(uint4), s));  // sentinel: ends every fixup walk
       uint32_t* d_nfix = reinterpret_cast<uint32_t*>(counters.p + 3);
-      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, p->cfirst.p, cgrp.p,
+      k_cb_chunks<<<grid_for(p->n_chunks, 128), 128, 0, s>>>(goff.p, p->poff.p, p->nrows.p, gbeg.p, cfirst.p, cgrp.p,
                                                            p->KB, p->n_chunks, p->chunks.p, p->tail_slot.p,
                                                            p->fix_list.p, d_nfix);
       GB_CUDA(cudaGetLastError());
@@ -1263,9 +1268,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_TRY(p->tail_slot.alloc(1));
       GB_TRY(p->fix_list.alloc(1));
       GB_TRY(p->side.alloc(2));
-      GB_TRY(p->cfirst.alloc(1));
-      GB_TRY(p->cta_range.alloc(1));
+      GB_TRY(p->tasks.alloc(1));
     }
+    GB_TRY(p->task_ctr.alloc(1));
+    GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
     GB_TRY(p->partial.alloc(std::max<uint64_t>(p->S, 1)));
     GB_CUDA(cudaMemsetAsync(p->partial.p, 0, std::max<uint64_t>(p->S, 1) * 4, s));
     GB_TRY(p->rem.alloc(std::max<uint32_t>(p->n_cb, 1)));
@@ -1287,8 +1293,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     }
     const uint64_t want_sell = ((uint64_t)p->num_slices + PR_SELL_THREADS / 32 - 1) / (PR_SELL_THREADS / 32);
     p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * 2);
-    p->n_fin_warp = p->KB > FIN_WARP_BLOCKS ? std::min<uint32_t>(p->n_cb, (h_nrows[FIN_WARP_BLOCKS] + 31) / 32 * 32) : 0;
-    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp + (p->n_cb - p->n_fin_warp + 31) / 32;
+    p->n_fin_warp = p->KB > FIN_CTA_BLOCKS ? std::min<uint32_t>(p->n_cb, (h_nrows[FIN_CTA_BLOCKS] + 31) / 32 * 32) : 0;
+    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_cb - p->n_fin_warp + 31) / 32;
     const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
     const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
@@ -1330,8 +1336,9 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.side = p->side.p;
   a.fix_list = p->fix_list.p;
   a.n_fix = p->n_fix;
-  a.cfirst = p->cfirst.p;
-  a.cta_range = p->cta_range.p;
+  a.tasks = p->tasks.p;
+  a.n_tasks = p->n_tasks;
+  a.task_ctr = p->task_ctr.p;
   a.rem = p->rem.p;
   a.fin_kb = p->fin_kb.p;
   a.sell = p->sell.p;
@@ -1419,6 +1426,7 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
   k_pr_init<<<grid_for(n, 256), 256, 0, s>>>(n, p->n_active, init, base, p->deal, p->outdeg.p, p->x[0].p, p->x[1].p,
                                             p->scores.p);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   g->timing.kernel_launches += 1;
 
   PrArgs a = make_args(p, base, cfg->damping_factor, cfg->tolerance);
@@ -1583,6 +1591,7 @@ gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0,
   gb::k_pr_init<<<gb::grid_for(p->n, 256), 256, 0, s>>>(p->n, p->n_active, init, base, p->deal, p->outdeg.p, d_x0,
                                                        d_x1, d_scores);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }
@@ -1651,7 +1660,7 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
   stats->segments = p->S;
   stats->groups = p->NG;
   stats->chunks = p->n_chunks;
-  stats->tasks = p->grid_cb;
+  stats->tasks = p->n_tasks;
   stats->cut_segments = p->n_fix;
   stats->chunk_groups = p->chunk_groups;
   stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) + (p->grid_cb && p->n_fix ? 1 : 0);
