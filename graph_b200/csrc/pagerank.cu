@@ -49,11 +49,11 @@ constexpr int PR_SELL_THREADS = 512; // SELL kernel: two 16-warp CTAs per SM and
 constexpr int PR_FIN_THREADS = 256;
 constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;  // sweeps bracketed by CUDA events when profiling is on
 constexpr uint32_t CB_G = 4;                 // block-local ids per group (one 64-bit load per lane)
-constexpr uint32_t CB_BLOCK_DEFAULT = 32768; // source-vector entries per block (128 KB of shared memory)
+constexpr uint32_t CB_BLOCK_DEFAULT = 49152; // source-vector entries per block (192 KB of shared memory)
 constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
-constexpr double CB_TAU_DEFAULT = 3.0;       // a (row, block) pair gets a segment if it expects >= tau edges
+constexpr double CB_TAU_DEFAULT = 2.0;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
-constexpr uint32_t CB_TASK_CHUNKS = 64;      // chunks per task (two per warp)
+constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
 // chunk flags (bits 24.. of PrChunk.w)
@@ -854,25 +854,41 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     }
     __syncthreads();
   }
-  // all other rows with segments: one lane per row
-  const uint32_t tail_warps = (a.n_cb - a.n_fin_warp + 31) / 32;
-  for (uint32_t w = gw; w < tail_warps; w += nw) {
-    const uint32_t l0 = a.n_fin_warp + 32 * w, l = l0 + lane;
-    const bool on = l < a.n_cb;
-    float old = 0.0f;
-    uint32_t deg = 1, gr = 0;
-    double s = 0.0;
-    if (on) {
-      gr = deal_global(l, P, pp);
-      old = a.scores[gr];
-      deg = a.outdeg[gr];
-      s = (double)a.rem[l];
+  // all other rows with segments: one lane per row, FIN_U consecutive 32-row groups per warp iteration
+  // (the loads of the groups are independent: the walk is latency bound, not bandwidth bound)
+  constexpr uint32_t FIN_U = 4;
+  const uint32_t tail_groups = (a.n_cb - a.n_fin_warp + 31) / 32;
+  for (uint32_t w = gw * FIN_U; w < tail_groups; w += nw * FIN_U) {
+    const uint32_t l0 = a.n_fin_warp + 32 * w;
+    const uint32_t kb = __ldg(a.fin_kb + (l0 >> 5));  // blocks of the first row (it has the most)
+    uint32_t l[FIN_U], gr[FIN_U], deg[FIN_U];
+    float old[FIN_U];
+    double s[FIN_U];
+#pragma unroll
+    for (uint32_t u = 0; u < FIN_U; ++u) {
+      l[u] = l0 + 32 * u + lane;
+      gr[u] = 0;
+      deg[u] = 1;
+      old[u] = 0.0f;
+      s[u] = 0.0;
+      if (l[u] < a.n_cb) {
+        gr[u] = deal_global(l[u], P, pp);
+        old[u] = a.scores[gr[u]];
+        deg[u] = a.outdeg[gr[u]];
+        s[u] = (double)a.rem[l[u]];
+      }
     }
-    const uint32_t kb = __ldg(a.fin_kb + (l0 >> 5));  // blocks of the warp's first row (it has the most)
-#pragma unroll 8
-    for (uint32_t j = 0; j < kb; ++j)
-      if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
-    if (on) err += pr_update<PEERS>(gr, (float)s, old, deg, a);
+#pragma unroll 2
+    for (uint32_t j = 0; j < kb; ++j) {
+      const uint32_t nr = __ldg(a.nrows + j);
+      const float* __restrict__ pj = a.partial + __ldg(a.poff + j);
+#pragma unroll
+      for (uint32_t u = 0; u < FIN_U; ++u)
+        if (l[u] < nr) s[u] += (double)pj[l[u]];
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < FIN_U; ++u)
+      if (l[u] < a.n_cb) err += pr_update<PEERS>(gr[u], (float)s[u], old[u], deg[u], a);
   }
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
@@ -1226,11 +1242,12 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<uint32_t> h_gbeg(p->KB + 1);
       GB_CUDA(cudaMemcpyAsync(h_gbeg.data(), gbeg.p, (size_t)(p->KB + 1) * 4, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      // ~10 tasks per SM keep the dynamic schedule level; a task is 64 chunks (two per warp) of at most
-      // 2048 groups; a thin block is cut into >= 64 chunks (down to one 64-group step each) so that all
-      // warps share it — a lone warp runs at its dependency latency, ~10x below the SM's throughput
+      // ~8 tasks per SM keep the dynamic schedule level; a task is 32 chunks (one per warp) of 512..2048
+      // groups (fewer, longer chunks = fewer segments cut by chunk boundaries); a thin block is cut into
+      // >= 64 chunks (down to one 64-group step each) so that all warps share it — a lone warp runs at
+      // its dependency latency, ~10x below the SM's throughput
       uint32_t C = env_u32("GB_PR_CHUNK", 0);
-      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 10 * CB_TASK_CHUNKS), 64), 2048);
+      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 8 * CB_TASK_CHUNKS), 512), 2048);
       C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
       p->chunk_groups = C;
       std::vector<uint32_t> h_cfirst(p->KB + 1, 0), h_cgrp(p->KB, C);
@@ -1284,8 +1301,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     p->smem_cb = ((size_t)B + 4) * sizeof(float);
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
     GB_CUDA(cudaFuncSetAttribute(k_pr_cb_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
-    // dual mode needs both kernels to have work; GB_PR_DUAL=0 runs them back to back on one stream
-    p->dual = p->grid_cb > 0 && p->num_slices > 0 && env_u32("GB_PR_DUAL", 1) != 0;
+    // GB_PR_DUAL=1 (experiment): k_pr_cb_half and k_pr_sell at the same time on two streams.  Measured
+    // (profiles/r02_sweep_breakdown.txt): both kernels load the same LSU data pipe, so the overlap buys
+    // <= 5 % at a 128 KB block and loses with larger blocks (k_pr_sell then starves for L1); default off.
+    p->dual = p->grid_cb > 0 && p->num_slices > 0 && env_u32("GB_PR_DUAL", 0) != 0;
     if (p->dual) {
       GB_CUDA(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
       GB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -1294,7 +1313,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     const uint64_t want_sell = ((uint64_t)p->num_slices + PR_SELL_THREADS / 32 - 1) / (PR_SELL_THREADS / 32);
     p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * 2);
     p->n_fin_warp = p->KB > FIN_CTA_BLOCKS ? std::min<uint32_t>(p->n_cb, (h_nrows[FIN_CTA_BLOCKS] + 31) / 32 * 32) : 0;
-    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_cb - p->n_fin_warp + 31) / 32;
+    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_cb - p->n_fin_warp + 127) / 128;
     const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
     const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
