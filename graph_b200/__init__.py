@@ -185,6 +185,14 @@ def _read_edge_list(path, with_values=False):
     return (src, dst, w) if with_values else (src, dst)
 
 
+def _check_host_csr(off: np.ndarray, tgt: np.ndarray, what: str) -> None:
+    """The C side reads off[n] and copies off[n] targets: reject arrays that are too short here."""
+    if off.ndim != 1 or len(off) < 2:
+        raise ValueError(f"{what} offsets need node_count + 1 >= 2 entries")
+    if tgt.ndim != 1 or len(tgt) < int(off[-1]):
+        raise ValueError(f"{what} targets hold {len(tgt)} entries but the offsets end at {int(off[-1])}")
+
+
 def _edges_from_numpy(arr) -> tuple[np.ndarray, np.ndarray]:
     a = np.asarray(arr)
     if a.ndim != 2 or a.shape[1] < 2:
@@ -349,6 +357,12 @@ class DiGraph(_Handle):
         io = np.ascontiguousarray(in_offsets, np.uint32)
         it = np.ascontiguousarray(in_targets, np.uint32)
         ow = None if out_weights is None else np.ascontiguousarray(out_weights, np.float32)
+        _check_host_csr(oo, ot, "out")
+        _check_host_csr(io, it, "in")
+        if len(io) != len(oo):
+            raise ValueError("in and out offsets must have the same length (node_count + 1)")
+        if ow is not None and len(ow) != len(ot):
+            raise ValueError("out_weights must have one entry per out target")
         out = C.c_void_p()
 
         def go():
@@ -504,6 +518,7 @@ class Graph(_Handle):
     def from_csr(offsets, targets) -> "Graph":
         off = np.ascontiguousarray(offsets, np.uint32)
         tgt = np.ascontiguousarray(targets, np.uint32)
+        _check_host_csr(off, tgt, "undirected")
         out = C.c_void_p()
 
         def go():

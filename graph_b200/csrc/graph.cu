@@ -269,8 +269,15 @@ gb_status build_csr_device(cudaStream_t s, uint32_t n, uint32_t* d_rows, uint32_
                                        (int64_t)count, s));
     if (order) {
       GB_TRY(order_c.alloc(count));
-      GB_CUDA(cub::DeviceSelect::Flagged(sel_tmp.p, sel_bytes, order, flags.p, order_c.p, d_num.p,
+      // the uint32 selection has its own temporary-storage size: query it (never reuse the uint64 one)
+      size_t sel_bytes32 = 0;
+      GB_CUDA(cub::DeviceSelect::Flagged(nullptr, sel_bytes32, order, flags.p, order_c.p, d_num.p,
                                          (int64_t)count, s));
+      DevBuf<uint8_t> sel_tmp32;
+      GB_TRY(sel_tmp32.alloc(sel_bytes32));
+      GB_CUDA(cub::DeviceSelect::Flagged(sel_tmp32.p, sel_bytes32, order, flags.p, order_c.p, d_num.p,
+                                         (int64_t)count, s));
+      GB_CUDA(cudaStreamSynchronize(s));  // sel_tmp32 is released at the end of this scope
       order = order_c.p;
     }
     GB_CUDA(cudaMemcpyAsync(&out_count, d_num.p, 8, cudaMemcpyDeviceToHost, s));

@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     const uint32_t l = g * 32 + lane;
     const uint32_t kb = __ldg(a.fin_kb + g);  // blocks of the group's first row (it has the most)
     double s = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t j = warp; j < kb; j += FIN_WARPS)
       if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     part[warp][lane] = s;
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
         s[u] = (double)a.rem[l[u]];
       }
     }
-#pragma unroll 2
+#pragma unroll 4
     for (uint32_t j = 0; j < kb; ++j) {
       const uint32_t nr = __ldg(a.nrows + j);
       const float* __restrict__ pj = a.partial + __ldg(a.poff + j);

@@ -34,31 +34,46 @@ __global__ void k_sssp_init(uint32_t* __restrict__ dist, uint32_t n, uint32_t st
 // queue slot reservation, aggregated over the lanes that are appending right now: one atomicAdd per
 // group of converged lanes instead of one per successful relaxation (a single hot counter otherwise
 // serialises every append of the pass)
+// Lanes are grouped BY COUNTER (match_any on the pointer): callers append to different queues from
+// sibling branches, and nothing guarantees that the active mask holds lanes of one branch only.
 __device__ __forceinline__ uint32_t sssp_reserve(uint32_t* counter) {
   const unsigned active = __activemask();
-  const int leader = __ffs(active) - 1;
+  const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
+  const int leader = __ffs(peers) - 1;
   const uint32_t lane = threadIdx.x & 31;
   uint32_t base = 0;
-  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(active));
-  base = __shfl_sync(active, base, leader);
-  return base + __popc(active & ((1u << lane) - 1u));
+  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// A vertex whose distance improves several times in one pass (or several times while it waits in the far
+// pile) is queued once: near_stamp[t] holds the last pass, far_stamp[t] the last bucket epoch, in which t
+// was appended.  This bounds the near queue by n and the far pile by 2n whatever delta is.
+struct SsspStamps {
+  uint32_t* near_stamp;
+  uint32_t* far_stamp;
+  uint32_t pass, epoch;
+};
 __device__ __forceinline__ void sssp_relax_edge(const uint32_t* __restrict__ tgt, const float* __restrict__ w,
                                                 uint32_t* dist, uint32_t i, float du, float upper,
                                                 uint32_t* __restrict__ near_out, uint32_t* __restrict__ far,
-                                                uint32_t* counts, uint32_t cap) {
+                                                uint32_t* counts, uint32_t cap, const SsspStamps& st) {
   const uint32_t t = tgt[i];
   const float nd = __fadd_rn(du, w[i]);
   const uint32_t nb = __float_as_uint(nd);
   const uint32_t old = atomicMin(dist + t, nb);  // the CAS-min loop of sssp.rs:184-202
   if (nb < old) {
     if (nd < upper) {
-      const uint32_t pos = sssp_reserve(counts + 0);
-      if (pos < cap) near_out[pos] = t;
+      if (atomicMax(st.near_stamp + t, st.pass) < st.pass) {
+        const uint32_t pos = sssp_reserve(counts + 0);
+        if (pos < cap) near_out[pos] = t;
+      }
     } else {
-      const uint32_t pos = sssp_reserve(counts + 1);
-      if (pos < cap) far[pos] = t;
+      if (atomicMax(st.far_stamp + t, st.epoch) < st.epoch) {
+        const uint32_t pos = sssp_reserve(counts + 1);
+        if (pos < cap) far[pos] = t;
+      }
     }
   }
 }
@@ -66,7 +81,7 @@ __device__ __forceinline__ void sssp_relax_edge(const uint32_t* __restrict__ tgt
 __global__ void k_sssp_relax(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt,
                              const float* __restrict__ w, uint32_t* dist, const uint32_t* __restrict__ queue,
                              uint32_t count, float lower, float upper, uint32_t* __restrict__ near_out,
-                             uint32_t* __restrict__ far, uint32_t* counts, uint32_t cap) {
+                             uint32_t* __restrict__ far, uint32_t* counts, uint32_t cap, const SsspStamps st) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   for (uint32_t qb = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; qb < count; qb += nthreads) {
@@ -86,14 +101,15 @@ __global__ void k_sssp_relax(const uint32_t* __restrict__ off, const uint32_t* _
     }
     const bool small = live && (e - b) <= 8;
     if (small)
-      for (uint32_t i = b; i < e; ++i) sssp_relax_edge(tgt, w, dist, i, du, upper, near_out, far, counts, cap);
+      for (uint32_t i = b; i < e; ++i) sssp_relax_edge(tgt, w, dist, i, du, upper, near_out, far, counts, cap, st);
     unsigned mask = __ballot_sync(0xFFFFFFFFu, live && !small);
     while (mask) {
       const int owner = __ffs(mask) - 1;
       mask &= mask - 1;
       const uint32_t ob = __shfl_sync(0xFFFFFFFFu, b, owner), oe = __shfl_sync(0xFFFFFFFFu, e, owner);
       const float odu = __shfl_sync(0xFFFFFFFFu, du, owner);
-      for (uint32_t i = ob + lane; i < oe; i += 32) sssp_relax_edge(tgt, w, dist, i, odu, upper, near_out, far, counts, cap);
+      for (uint32_t i = ob + lane; i < oe; i += 32)
+        sssp_relax_edge(tgt, w, dist, i, odu, upper, near_out, far, counts, cap, st);
     }
   }
 }
@@ -147,11 +163,18 @@ static gb_status sssp_impl(const gb_graph* g, const gb_sssp_config* cfg, float* 
     d_dist = tmp.p;
   }
   uint32_t* dist = reinterpret_cast<uint32_t*>(d_dist);
-  // every successful relaxation appends one entry, so a queue never holds more than the number of
-  // improvements of one pass; m + n bounds a pass, and overflow is detected (cap) and reported.
-  const uint64_t cap64 = std::min<uint64_t>(m + n + 1024, 0xFFFFFFF0ull);
+  // a vertex is appended at most once per pass to the near queue and once per bucket epoch to the far pile
+  // (stamps), and the pile carried over a bucket change holds each vertex at most once more: 2n bounds
+  // every queue for every delta (the overflow check below is an internal-error guard only)
+  (void)m;
+  const uint64_t cap64 = std::min<uint64_t>(2ull * n + 1024, 0xFFFFFFF0ull);
   const uint32_t cap = (uint32_t)cap64;
-  DevBuf<uint32_t> qa, qb, fa, fb, counts, minb;
+  DevBuf<uint32_t> qa, qb, fa, fb, counts, minb, near_stamp, far_stamp;
+  GB_TRY(near_stamp.alloc(n));
+  GB_TRY(far_stamp.alloc(n));
+  GB_CUDA(cudaMemsetAsync(near_stamp.p, 0, (size_t)n * 4, s));
+  GB_CUDA(cudaMemsetAsync(far_stamp.p, 0, (size_t)n * 4, s));
+  SsspStamps st{near_stamp.p, far_stamp.p, 0u, 1u};
   GB_TRY(qa.alloc(cap));
   GB_TRY(qb.alloc(cap));
   GB_TRY(fa.alloc(cap));
@@ -180,9 +203,10 @@ static gb_status sssp_impl(const gb_graph* g, const gb_sssp_config* cfg, float* 
     while (near_count > 0) {
       const uint32_t zero2[2] = {0u, far_count};
       GB_CUDA(cudaMemcpyAsync(counts.p, zero2, 8, cudaMemcpyHostToDevice, s));
+      st.pass += 1;
       k_sssp_relax<<<grid_for((uint64_t)near_count, blk), blk, 0, s>>>(
           g->out.off.p, g->out.tgt.p, g->out.w.p, dist, near_in, near_count, lower, upper, near_out, far,
-          counts.p, cap);
+          counts.p, cap, st);
       g->timing.kernel_launches += 1;
       GB_CUDA(cudaMemcpyAsync(h_counts, counts.p, 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
@@ -210,6 +234,7 @@ static gb_status sssp_impl(const gb_graph* g, const gb_sssp_config* cfg, float* 
     while (!(dmin < delta * (float)(next_bucket + 1.0))) next_bucket += 1.0;
     while (next_bucket > bucket + 1.0 && dmin < delta * (float)next_bucket) next_bucket -= 1.0;
     bucket = next_bucket;
+    st.epoch += 1;  // entries appended to the pile from now on are tracked under the new epoch
     const float lo2 = delta * (float)bucket, up2 = delta * (float)(bucket + 1.0);
     const uint32_t zero3[3] = {0u, 0u, 0u};
     GB_CUDA(cudaMemcpyAsync(counts.p, zero3, 12, cudaMemcpyHostToDevice, s));

@@ -183,6 +183,9 @@ class GraphBuilder {
   GraphBuilder& node_count(std::uint32_t n) { n_ = n; return *this; }
   // file_format(format).path(p): read the file with the library's native readers (csrc/io.cu)
   GraphBuilder& file_format(FileFormat f) { format_ = f; return *this; }
+  // read the third column of a text edge list as f32 edge values (the reference selects this through
+  // the graph type's EV parameter: DirectedCsrGraph<u32, (), f32>)
+  GraphBuilder& with_values(bool on = true) { with_values_ = on; return *this; }
   GraphBuilder& path(const std::string& p) {
     std::ifstream in(p, std::ios::binary);
     if (!in) throw Error(GB_ERR_INVALID, "cannot open " + p);  // Error::IoError, lib.rs:276-281
@@ -197,7 +200,11 @@ class GraphBuilder {
       detail::check(gb_edge_list_parse(bytes.data(), bytes.size(), nullptr, nullptr, nullptr, &m));
       src_.resize(m);
       dst_.resize(m);
-      detail::check(gb_edge_list_parse(bytes.data(), bytes.size(), src_.data(), dst_.data(), nullptr, &m));
+      // the value column travels with the edges when the builder was asked for values (EV = f32,
+      // edgelist.rs:237-241: a missing value is EV::default())
+      if (with_values_) w_.resize(m);
+      detail::check(gb_edge_list_parse(bytes.data(), bytes.size(), src_.data(), dst_.data(),
+                                       with_values_ ? w_.data() : nullptr, &m));
       n_ = 0;  // max id + 1
     }
     return *this;
@@ -207,6 +214,7 @@ class GraphBuilder {
   std::uint32_t pending_node_count() const { return n_; }  // 0 = "max id + 1" at build time
   const std::vector<std::uint32_t>& pending_sources() const { return src_; }
   const std::vector<std::uint32_t>& pending_targets() const { return dst_; }
+  const std::vector<float>& pending_values() const { return w_; }
   DirectedCsrGraph build_directed() const {
     gb_graph* g = nullptr;
     detail::check(gb_digraph_from_edges_u32(device_, src_.data(), dst_.data(), w_.empty() ? nullptr : w_.data(), src_.size(), n_,
@@ -222,6 +230,7 @@ class GraphBuilder {
  private:
   CsrLayout layout_ = CsrLayout::Unsorted;  // CsrLayout::default()
   FileFormat format_ = FileFormat::EdgeList;
+  bool with_values_ = false;
   int device_ = 0;
   std::uint32_t n_ = 0;
   std::vector<std::uint32_t> src_, dst_;

@@ -30,6 +30,12 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 6; ++i) EXPECT(b.pending_sources()[i] == s[i] && b.pending_targets()[i] == t[i]);
   b.path(dir + "/windows.el");  // CRLF line ends
   EXPECT(b.pending_edge_count() == 3 && b.pending_sources()[2] == 1 && b.pending_targets()[2] == 3);
+  // weighted edge list: the value column is kept when asked for, dropped otherwise
+  b.with_values().path(dir + "/test.wel");
+  EXPECT(b.pending_edge_count() == 6 && b.pending_values().size() == 6);
+  EXPECT(b.pending_values()[0] == 0.1f && b.pending_values()[5] == 0.6f);
+  b.with_values(false).path(dir + "/test.wel");
+  EXPECT(b.pending_edge_count() == 6 && b.pending_values().empty());
   bool threw = false;
   try { b.path(dir + "/does_not_exist.el"); } catch (const graph::Error&) { threw = true; }
   EXPECT(threw);

@@ -85,6 +85,46 @@ def test_edge_list_reader(golden_dir):
     assert (src == o[0]).all() and (dst == o[1]).all() and (w == o[2]).all()
 
 
+def test_edge_list_reader_is_bounded_by_the_buffer(tmp_path):
+    """The parser works on (pointer, length): no trailing newline, a trailing space and a missing value
+    must neither read past the buffer nor pull the next line's numbers into this line's value."""
+    import ctypes as C
+    import graph_b200 as gb
+    from graph_b200._capi import lib, check
+
+    def parse(text: bytes):
+        # the buffer handed over is exactly len(text) bytes, followed by bytes that must not be read
+        buf = C.create_string_buffer(text + b"9999", len(text) + 4)
+        m = C.c_uint64(0)
+        check(lib.gb_edge_list_parse(buf, len(text), None, None, None, C.byref(m)))
+        src, dst, w = np.empty(m.value, np.uint32), np.empty(m.value, np.uint32), np.empty(m.value, np.float32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib.gb_edge_list_parse(buf, len(text), P(src), P(dst), P(w), C.byref(m)))
+        return list(zip(src.tolist(), dst.tolist(), w.tolist()))
+
+    assert parse(b"0 1 2.5\n3 4 1.5") == [(0, 1, 2.5), (3, 4, 1.5)]          # no trailing newline
+    assert parse(b"0 1 \n3 4") == [(0, 1, 0.0), (3, 4, 0.0)]                  # trailing space, value missing
+    assert parse(b"0 1 7") == [(0, 1, 7.0)]                                    # value ends at the buffer end
+    assert parse(b"5 6 1e-3\r\n7 8 +2\r\n") == [(5, 6, float(np.float32(0.001))), (7, 8, 2.0)]  # CRLF, exponent, +
+    assert parse(b"1 2 0.25xyz\n3 4 5\n") == [(1, 2, 0.25), (3, 4, 5.0)]     # longest valid prefix (parse_partial)
+
+
+def test_from_csr_rejects_short_arrays():
+    import graph_b200 as gb
+    off = np.array([0, 1, 2], np.uint32)
+    tgt = np.array([1, 0], np.uint32)
+    with pytest.raises(ValueError):
+        gb.DiGraph.from_csr(np.array([], np.uint32), tgt, off, tgt)            # empty offsets
+    with pytest.raises(ValueError):
+        gb.DiGraph.from_csr(off, tgt, off[:2], tgt)                            # in offsets shorter than out
+    with pytest.raises(ValueError):
+        gb.DiGraph.from_csr(off, tgt[:1], off, tgt)                            # targets shorter than offsets[n]
+    with pytest.raises(ValueError):
+        gb.DiGraph.from_csr(off, tgt, off, tgt, out_weights=np.ones(1, np.float32))
+    with pytest.raises(ValueError):
+        gb.Graph.from_csr(off, tgt[:1])
+
+
 def test_from_numpy_argument_checks():
     import graph_b200 as gb
     with pytest.raises(TypeError, match="2-dimensional array with at least 2 columns"):
