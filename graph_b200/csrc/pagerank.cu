@@ -922,6 +922,44 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   }
 }
 
+// ---- inter-sweep barrier of the sharded path, on the device -------------------------------------------
+// Every rank owns a control block in peer-mapped (symmetric) memory: arrive[q] = the last sweep rank q has
+// finished, errs[sweep & 1][q] = rank q's share of that sweep's error.  After its finish kernel a rank
+// publishes its error share and then its arrival into EVERY rank's block (release, system scope), waits
+// until all ranks have arrived at this sweep (acquire) and adds the P shares in rank order — every rank
+// gets the same total, without a host round trip or a collective.  Two error banks suffice: a rank can
+// be at most one sweep ahead of the slowest (it cannot pass barrier k+1 before everyone left barrier k).
+struct PrSyncBlock {
+  uint32_t arrive[8];
+  double errs[2][8];
+};
+__global__ void k_pr_sync(PrSyncBlock* self, PrSyncBlock* const* peers_dev, uint32_t P, uint32_t rank,
+                          uint32_t sweep_no, const double* __restrict__ local_err, double* __restrict__ total_err,
+                          uint32_t slot) {
+  const uint32_t q = threadIdx.x;
+  const double mine = *local_err;
+  __threadfence_system();  // this rank's stores of the sweep (previous kernels) before its arrival
+  if (q < P) {
+    PrSyncBlock* dst = (q == rank) ? self : peers_dev[q];
+    volatile double* e = &dst->errs[sweep_no & 1u][rank];
+    *e = mine;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->arrive[rank]), "r"(sweep_no) : "memory");
+  }
+  if (q < P) {
+    uint32_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&self->arrive[q]) : "memory");
+    } while ((int32_t)(seen - sweep_no) < 0);
+  }
+  __syncthreads();
+  if (q == 0) {
+    double t = 0.0;
+    for (uint32_t r = 0; r < P; ++r) t += ((volatile double*)self->errs[sweep_no & 1u])[r];
+    total_err[slot] = t;
+  }
+}
+
 // own == 0: scores of rows this rank does not own stay 0 so that the ranks' vectors can be summed
 __global__ void k_pr_init(uint32_t n, uint32_t n_active, float init, float base, PrDeal deal,
                           const uint32_t* __restrict__ outdeg, float* __restrict__ x0,
@@ -1563,6 +1601,8 @@ static gb_status page_rank_impl(const gb_graph* g, const gb_page_rank_config* cf
 struct gb_pr_shard {
   const gb_graph* graph = nullptr;
   gb::PrPlan* plan = nullptr;
+  gb::DevBuf<void*> sync_table;       // device copy of the ranks' control-block pointers (gb_pr_shard_sync)
+  void* sync_table_host[8] = {nullptr};
 };
 
 extern "C" {
@@ -1649,6 +1689,32 @@ gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t swe
   if (sweep_no == 1 && p->n_active < p->n)
     gb::k_pr_fill_inactive<<<gb::grid_for(p->n - p->n_active, 256), 256, 0, s>>>(
         p->n, p->n_active, base, p->outdeg.p, const_cast<float*>(d_x_cur));
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+gb_status gb_pr_shard_sync(const gb_pr_shard* shard, uint64_t sweep_no, const double* d_local_error,
+                           void* d_self_block, void* const* d_peer_blocks, double* d_total_error,
+                           uint32_t slot, void* cuda_stream) {
+  GB_REQUIRE(shard && d_local_error && d_self_block && d_total_error, "NULL argument");
+  const gb::PrPlan* p = shard->plan;
+  GB_REQUIRE(p->deal.P <= 8, "at most 8 ranks");
+  GB_REQUIRE(p->deal.P == 1 || d_peer_blocks, "peer block array is NULL");
+  GB_REQUIRE(sweep_no >= 1 && sweep_no < 0x7FFFFFFFull, "bad sweep number");
+  gb::DeviceGuard guard(shard->graph->device);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  // the peer pointer table lives in the shard (device copy, refreshed when the pointers change)
+  gb_pr_shard* sh = const_cast<gb_pr_shard*>(shard);
+  void* table[8] = {nullptr};
+  for (uint32_t q = 0; q < p->deal.P; ++q) table[q] = (q == p->deal.p) ? d_self_block : d_peer_blocks[q];
+  if (!sh->sync_table.p || memcmp(table, sh->sync_table_host, sizeof table) != 0) {
+    if (!sh->sync_table.p) GB_TRY(sh->sync_table.alloc(8));
+    memcpy(sh->sync_table_host, table, sizeof table);
+    GB_CUDA(cudaMemcpyAsync(sh->sync_table.p, table, sizeof table, cudaMemcpyHostToDevice, s));
+  }
+  gb::k_pr_sync<<<1, 32, 0, s>>>(static_cast<gb::PrSyncBlock*>(d_self_block),
+                                reinterpret_cast<gb::PrSyncBlock* const*>(sh->sync_table.p), p->deal.P, p->deal.p,
+                                (uint32_t)sweep_no, d_local_error, d_total_error, slot);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

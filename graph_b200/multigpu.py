@@ -8,9 +8,9 @@ sweeps its rows (`gb_pr_shard_step`) and the finished out_scores are exchanged e
 
   * "peer"      — fused: the sweep kernels store each finished out_score straight into every rank's
                   next vector — one `multimem.st` replicated by the NVSwitch when torch symmetric
-                  memory offers a multicast mapping, else one NVLink store per peer; the 8-byte
-                  all-reduce of the sweep error is the only collective and doubles as the inter-sweep
-                  barrier, or
+                  memory offers a multicast mapping, else one NVLink store per peer; the inter-sweep
+                  barrier and the sum of the ranks' error shares are one tiny kernel over peer-mapped
+                  control blocks (`gb_pr_shard_sync`): no collective and no host round trip per sweep, or
   * "allgather" — baseline: the own slices are packed and exchanged with one NCCL all-gather.
 
 `torch.distributed` is plumbing only; the compute is the same CUDA kernels as on one GPU.  The
@@ -82,6 +82,13 @@ class CudaShardBackend:
                                    C.c_void_p(scores.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()))
         self.launches += self.stats["launches_per_sweep"] + (1 if sweep_no == 1 else 0)
 
+    def sync(self, seq, err_local, self_block, peer_blocks, total_err, slot):
+        """Device-side barrier + error sum (gb_pr_shard_sync); peer_blocks has one entry per rank."""
+        arr = (C.c_void_p * len(peer_blocks))(*peer_blocks)
+        check(lib.gb_pr_shard_sync(self._shard, seq, C.c_void_p(err_local.data_ptr()), C.c_void_p(self_block), arr,
+                                   C.c_void_p(total_err.data_ptr()), slot, self._stream()))
+        self.launches += 1
+
     def finish(self, scores_internal):
         out = torch.empty_like(scores_internal)
         check(lib.gb_pr_shard_finish(self._shard, C.c_void_p(scores_internal.data_ptr()), C.c_void_p(out.data_ptr()),
@@ -136,12 +143,18 @@ class ShardedPageRank:
     def _setup_symmetric(self, dev, multicast):
         import torch.distributed._symmetric_memory as symm_mem
         group_name = (self.group or dist.group.WORLD).group_name
-        buf = symm_mem.empty(2 * self.n_pad, dtype=torch.float32, device=dev)
+        ctl_floats = 64  # this rank's 192-byte control block of the device-side barrier (gb_pr_shard_sync)
+        buf = symm_mem.empty(2 * self.n_pad + ctl_floats, dtype=torch.float32, device=dev)
         hdl = symm_mem.rendezvous(buf, group_name)
         self._symm = (buf, hdl)
         buf.zero_()
-        self.x = [buf[: self.n_pad], buf[self.n_pad:]]
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)   # every control block is zero before anybody publishes into it
+        self.x = [buf[: self.n_pad], buf[self.n_pad: 2 * self.n_pad]]
         ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._sync_blocks = [p + 2 * self.n_pad * 4 for p in ptrs]
+        self._sync_seq = 0
+        self._total_err = torch.zeros(64, dtype=torch.float64, device=dev)
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if multicast else 0
         self.multicast = mc != 0
         for which in (0, 1):
@@ -169,8 +182,10 @@ class ShardedPageRank:
     def run(self, max_iterations: int = 20, damping: float = 0.85, tolerance: float = 0.0):
         b = self.backend
         b.init(damping, self.x[0][: self.n], self.x[1][: self.n], self.scores)
-        if self.exchange == "peer":
-            dist.barrier(group=self.group)  # nobody may store into a peer that is still initialising
+        # fused exchange: no barrier is needed before sweep 1 — a peer's init and this rank's sweep-1
+        # stores touch disjoint entries (init writes x0, scores and the rows without in-edges of x1), and
+        # every later hazard is ordered by the device barrier that ends each sweep
+        device_sync = self.exchange == "peer" and hasattr(b, "sync")
         sweep = 0
         limit = max_iterations if max_iterations else 100000
         diag = self.diag
@@ -194,16 +209,25 @@ class ShardedPageRank:
                 diag.append(ev)
             # total error of the sweep; also the barrier that orders the peer stores of sweep k before
             # any rank's reads in sweep k+1
-            dist.all_reduce(self.err, op=dist.ReduceOp.SUM, group=self.group)
+            if device_sync:
+                slot = sweep % 64
+                b.sync(self._sync_seq + sweep, self.err, self._sync_blocks[self.rank], self._sync_blocks,
+                       self._total_err, slot)
+                total = self._total_err[slot]
+            else:
+                dist.all_reduce(self.err, op=dist.ReduceOp.SUM, group=self.group)
+                total = self.err[0]
             if tolerance > 0.0:
-                self.error = float(self.err.item())
+                self.error = float(total.item())
                 if self.error < tolerance:
                     break
             if sweep == limit:
                 break
         self.ran_iterations = sweep
+        if device_sync:
+            self._sync_seq += sweep
         if not tolerance > 0.0:
-            self.error = float(self.err.item())
+            self.error = float(total.item())
         return self
 
     def diag_summary(self):

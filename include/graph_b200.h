@@ -278,6 +278,16 @@ gb_status gb_pr_shard_step(const gb_pr_shard* shard, float damping, uint64_t swe
                            const float* d_x_cur, float* d_x_next, float* const* d_peer_x_next,
                            uint32_t peer_count, float* d_mc_x_next, float* d_scores, double* d_error,
                            void* cuda_stream);
+/* Device-side inter-sweep barrier + error sum of the fused exchange (no collective, no host round trip).
+ * Every rank owns a 192-byte control block in peer-mapped memory (zero-initialised; d_self_block is this
+ * rank's, d_peer_blocks[q] the mapping of rank q's, entry `rank` ignored).  Enqueued after
+ * gb_pr_shard_step: publishes this rank's *d_local_error and its arrival at sweep_no into every rank's
+ * block, waits until all ranks have arrived, and stores the sum of the P error shares (added in rank
+ * order: identical on every rank) in d_total_error[slot]. */
+gb_status gb_pr_shard_sync(const gb_pr_shard* shard, uint64_t sweep_no, const double* d_local_error,
+                           void* d_self_block, void* const* d_peer_blocks, double* d_total_error,
+                           uint32_t slot, void* cuda_stream);
+#define GB_PR_SYNC_BLOCK_BYTES 192
 /* internal order -> original ids: d_scores_out[v] = d_scores_internal[new_id[v]] */
 gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_internal,
                              float* d_scores_out, void* cuda_stream);
