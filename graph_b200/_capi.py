@@ -13,6 +13,7 @@ LAYOUT_UNSORTED, LAYOUT_SORTED, LAYOUT_DEDUPLICATED = 0, 1, 2
 KIND_DIRECTED, KIND_UNDIRECTED = 0, 1
 CSR_OUT, CSR_IN, CSR_UNDIRECTED = 0, 1, 2
 PR_AUTO, PR_EXACT, PR_JACOBI = 0, 1, 2
+WCC_INIT, WCC_SAMPLE, WCC_COMPRESS, WCC_MERGE, WCC_LINK_REMAINING = range(5)
 
 
 class GraphInfo(C.Structure):
@@ -90,6 +91,9 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "gb_wcc": (C.c_int, [_P, C.POINTER(WccConfig), _P]),
     "gb_wcc_device": (C.c_int, [_P, C.POINTER(WccConfig), _P]),
+    "gb_wcc_shard_phase": (C.c_int, [_P, C.POINTER(WccConfig), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_int, _P, _P, _P]),
+    "gb_wcc_sample_label": (C.c_int, [_P, C.POINTER(WccConfig), _P, C.POINTER(C.c_uint32), C.POINTER(C.c_int), _P]),
     "gb_sssp": (C.c_int, [_P, C.POINTER(SsspConfig), _P]),
     "gb_sssp_device": (C.c_int, [_P, C.POINTER(SsspConfig), _P]),
     "gb_triangle_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),

@@ -39,9 +39,9 @@ __global__ void k_cc_init(uint32_t* __restrict__ parent, uint32_t n) {
 }
 
 // sample_subgraph, wcc.rs:186-204: link u with its first `rounds` out-neighbours
-__global__ void k_cc_sample(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t n,
-                            uint32_t rounds, uint32_t* parent) {
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+__global__ void k_cc_sample(const uint32_t* __restrict__ off, const uint32_t* __restrict__ tgt, uint32_t vb,
+                            uint32_t n, uint32_t rounds, uint32_t* parent) {
+  for (uint32_t u = vb + blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     const uint32_t b = off[u], e = off[u + 1];
     const uint32_t lim = (e - b < rounds) ? e : b + rounds;  // out_neighbors(u).take(neighbor_rounds)
     for (uint32_t i = b; i < lim; ++i) af_link(parent, u, tgt[i]);
@@ -75,13 +75,13 @@ __global__ void k_cc_sample_labels(const uint32_t* __restrict__ parent, uint32_t
 // link_remaining, wcc.rs:274-301: one warp per vertex outside the sampled giant component
 __global__ void k_cc_link_remaining(const uint32_t* __restrict__ out_off, const uint32_t* __restrict__ out_tgt,
                                     const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                                    uint32_t n, uint32_t rounds, uint32_t skip, int use_skip,
+                                    uint32_t vb, uint32_t n, uint32_t rounds, uint32_t skip, int use_skip,
                                     uint32_t* parent) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   // lanes first test 32 consecutive vertices, then the warp serves the survivors one by one
-  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+  for (uint32_t base = vb + warp * 32; base < n; base += nwarps * 32) {
     const uint32_t mine = base + lane;
     bool live = mine < n;
     uint32_t ob = 0, oe = 0, ib = 0, ie = 0;
@@ -116,6 +116,42 @@ __global__ void k_cc_link_remaining(const uint32_t* __restrict__ out_off, const 
   }
 }
 
+// the most frequent label among `sampling_size` pseudo-random vertices (fixed seed: every rank of a
+// sharded run that holds the same parent array picks the same label)
+static gb_status most_frequent_label(cudaStream_t s, const uint32_t* d_parent, uint32_t n, uint64_t sampling_size,
+                                     uint32_t* label, int* found) {
+  *label = 0;
+  *found = 0;
+  const uint32_t samples = (uint32_t)std::min<uint64_t>(sampling_size, 1u << 20);
+  if (samples == 0 || n == 0) return GB_OK;
+  DevBuf<uint32_t> d_samp;
+  GB_TRY(d_samp.alloc(samples));
+  k_cc_sample_labels<<<grid_for(samples, 256), 256, 0, s>>>(d_parent, n, samples, 0x5DEECE66Dull, d_samp.p);
+  std::vector<uint32_t> h(samples);
+  GB_CUDA(cudaMemcpyAsync(h.data(), d_samp.p, (size_t)samples * 4, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+  std::sort(h.begin(), h.end());
+  uint32_t best_cnt = 0, run = 0;
+  for (uint32_t i = 0; i < samples; ++i) {
+    run = (i > 0 && h[i] == h[i - 1]) ? run + 1 : 1;
+    if (run > best_cnt) {
+      best_cnt = run;
+      *label = h[i];
+    }
+  }
+  *found = 1;
+  return GB_OK;
+}
+
+// union of two forests over the same vertex set: every tree edge (v, other[v]) of the other forest is
+// linked into parent[] with the Afforest rule, so parent[] ends up connecting what either forest connected
+__global__ void k_cc_merge(uint32_t* parent, const uint32_t* __restrict__ other, uint32_t n) {
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const uint32_t o = other[v];
+    if (o != v) af_link(parent, v, o);
+  }
+}
+
 static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t* d_comp, uint32_t* h_comp) {
   GB_REQUIRE(g && cfg, "NULL argument");
   if (g->kind != GB_KIND_DIRECTED)
@@ -137,34 +173,16 @@ static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t*
   k_cc_init<<<grid, blk, 0, s>>>(d_comp, n);
   // sample_subgraph, wcc.rs:186-204: every vertex links its first `neighbor_rounds` out-neighbours
   const uint32_t sample_rounds = rounds;
-  if (sample_rounds) k_cc_sample<<<grid, blk, 0, s>>>(g->out.off.p, g->out.tgt.p, n, sample_rounds, d_comp);
+  if (sample_rounds) k_cc_sample<<<grid, blk, 0, s>>>(g->out.off.p, g->out.tgt.p, 0, n, sample_rounds, d_comp);
   k_cc_compress<<<grid, blk, 0, s>>>(d_comp, n);
   g->timing.kernel_launches += 2 + (sample_rounds ? 1 : 0);
   // find_largest_component, wcc.rs:245-271 (which component is skipped never changes the result)
   uint32_t skip = 0;
   int use_skip = 0;
-  const uint32_t samples = (uint32_t)std::min<uint64_t>(cfg->sampling_size, 1u << 20);
-  if (samples > 0 && n > 0) {
-    DevBuf<uint32_t> d_samp;
-    GB_TRY(d_samp.alloc(samples));
-    k_cc_sample_labels<<<grid_for(samples, blk), blk, 0, s>>>(d_comp, n, samples, 0x5DEECE66Dull, d_samp.p);
-    std::vector<uint32_t> h(samples);
-    GB_CUDA(cudaMemcpyAsync(h.data(), d_samp.p, (size_t)samples * 4, cudaMemcpyDeviceToHost, s));
-    GB_CUDA(cudaStreamSynchronize(s));
-    std::sort(h.begin(), h.end());
-    uint32_t best_cnt = 0, run = 0;
-    for (uint32_t i = 0; i < samples; ++i) {
-      run = (i > 0 && h[i] == h[i - 1]) ? run + 1 : 1;
-      if (run > best_cnt) {
-        best_cnt = run;
-        skip = h[i];
-      }
-    }
-    use_skip = 1;
-    g->timing.kernel_launches += 1;
-  }
+  GB_TRY(most_frequent_label(s, d_comp, n, cfg->sampling_size, &skip, &use_skip));
+  if (use_skip) g->timing.kernel_launches += 1;
   k_cc_link_remaining<<<grid_for((uint64_t)n, blk), blk, 0, s>>>(g->out.off.p, g->out.tgt.p, g->in.off.p,
-                                                               g->in.tgt.p, n, sample_rounds, skip, use_skip,
+                                                               g->in.tgt.p, 0, n, sample_rounds, skip, use_skip,
                                                                d_comp);
   k_cc_compress<<<grid, blk, 0, s>>>(d_comp, n);
   g->timing.kernel_launches += 2;
@@ -188,5 +206,54 @@ gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* c
 gb_status gb_wcc_device(const gb_graph* graph, const gb_wcc_config* config, uint32_t* d_components) {
   GB_REQUIRE(d_components != nullptr, "d_components is NULL");
   return gb::wcc_impl(graph, config, d_components, nullptr);
+}
+
+// ---- multi-GPU WCC: the phases of wcc() (wcc.rs:158-183) over one rank's vertex range ----------------
+gb_status gb_wcc_shard_phase(const gb_graph* g, const gb_wcc_config* cfg, uint32_t phase, uint32_t vertex_begin,
+                             uint32_t vertex_end, uint32_t skip_label, int use_skip, uint32_t* d_parent,
+                             const uint32_t* d_other, void* cuda_stream) {
+  GB_REQUIRE(g && cfg && d_parent, "NULL argument");
+  if (g->kind != GB_KIND_DIRECTED)
+    return gb::fail(GB_ERR_UNSUPPORTED, "wcc needs a directed graph (wcc.rs:130: DirectedNeighbors)");
+  GB_REQUIRE(vertex_begin <= vertex_end && vertex_end <= g->n, "bad vertex range [%u, %u)", vertex_begin, vertex_end);
+  gb::DeviceGuard guard(g->device);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t n = g->n, span = vertex_end - vertex_begin;
+  const unsigned blk = 256;
+  const uint32_t rounds = (uint32_t)std::min<uint64_t>(cfg->neighbor_rounds, 0xFFFFFFFFull);
+  switch (phase) {
+    case GB_WCC_INIT:
+      gb::k_cc_init<<<gb::grid_for(n, blk), blk, 0, s>>>(d_parent, n);
+      break;
+    case GB_WCC_SAMPLE:  // sample_subgraph over the rank's vertices
+      if (rounds && span)
+        gb::k_cc_sample<<<gb::grid_for(span, blk), blk, 0, s>>>(g->out.off.p, g->out.tgt.p, vertex_begin, vertex_end,
+                                                               rounds, d_parent);
+      break;
+    case GB_WCC_COMPRESS:
+      gb::k_cc_compress<<<gb::grid_for(n, blk), blk, 0, s>>>(d_parent, n);
+      break;
+    case GB_WCC_MERGE:  // union with another rank's forest
+      GB_REQUIRE(d_other != nullptr, "d_other is NULL");
+      gb::k_cc_merge<<<gb::grid_for(n, blk), blk, 0, s>>>(d_parent, d_other, n);
+      break;
+    case GB_WCC_LINK_REMAINING:  // link_remaining over the rank's vertices, skipping the GLOBAL giant component
+      if (span)
+        gb::k_cc_link_remaining<<<gb::grid_for((uint64_t)span, blk), blk, 0, s>>>(
+            g->out.off.p, g->out.tgt.p, g->in.off.p, g->in.tgt.p, vertex_begin, vertex_end, rounds, skip_label,
+            use_skip, d_parent);
+      break;
+    default:
+      return gb::fail(GB_ERR_INVALID, "unknown wcc shard phase %u", phase);
+  }
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+gb_status gb_wcc_sample_label(const gb_graph* g, const gb_wcc_config* cfg, const uint32_t* d_parent,
+                              uint32_t* label, int* found, void* cuda_stream) {
+  GB_REQUIRE(g && cfg && d_parent && label && found, "NULL argument");
+  gb::DeviceGuard guard(g->device);
+  return gb::most_frequent_label((cudaStream_t)cuda_stream, d_parent, g->n, cfg->sampling_size, label, found);
 }
 }

@@ -247,3 +247,86 @@ class ShardedPageRank:
 
     def scores_host(self) -> np.ndarray:
         return self.scores_device().cpu().numpy()
+
+
+# =====================================================================================================
+# Multi-GPU WCC (1-D cut by vertex range)
+# =====================================================================================================
+def vertex_ranges(n: int, world: int):
+    """Contiguous, 32-aligned vertex ranges of (almost) equal size; Graph500 ids are scrambled, so equal
+    ranges carry (almost) equal numbers of edges."""
+    cuts = [min(n, ((n * p // world) + 31) // 32 * 32) for p in range(world)] + [n]
+    return [(cuts[p], max(cuts[p], cuts[p + 1])) for p in range(world)]
+
+
+class CudaWccBackend:
+    """gb_wcc_shard_phase / gb_wcc_sample_label of libgraph_b200.so on this rank's GPU."""
+
+    def __init__(self, graph, neighbor_rounds=2, sampling_size=1024, chunk_size=16384):
+        self.graph = graph
+        self.n = graph.node_count()
+        self.cfg = _capi.WccConfig(chunk_size, neighbor_rounds, sampling_size)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.launches = 0
+
+    def new_parent(self):
+        return torch.empty(self.n, dtype=torch.int32, device=self.device)
+
+    def phase(self, which, parent, vb=0, ve=0, skip=0, use_skip=0, other=None):
+        check(lib.gb_wcc_shard_phase(self.graph._g, C.byref(self.cfg), which, vb, ve, skip, int(use_skip),
+                                     C.c_void_p(parent.data_ptr()),
+                                     C.c_void_p(other.data_ptr()) if other is not None else None,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.launches += 1
+
+    def sample_label(self, parent):
+        label, found = C.c_uint32(0), C.c_int(0)
+        check(lib.gb_wcc_sample_label(self.graph._g, C.byref(self.cfg), C.c_void_p(parent.data_ptr()),
+                                      C.byref(label), C.byref(found),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return int(label.value), bool(found.value)
+
+
+class ShardedWcc:
+    """wcc_afforest over `world` ranks: every rank runs the phases of wcc() (wcc.rs:158-183) on its
+    vertex range over a full parent[n]; the P forests are exchanged with one all-gather after the
+    sampling phase and one after link_remaining, and merged with the Afforest link rule, so every rank
+    ends with the same labels = minimum node id per component (bit-equal to the single-GPU result).
+
+    The giant component that link_remaining skips is chosen on the MERGED sampled forest: skipping a
+    vertex is only sound when both endpoints of each skipped edge are already connected or the other
+    endpoint is processed by its owner, which a rank-local choice cannot guarantee."""
+
+    def __init__(self, graph=None, backend=None, group=None, **cfg):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.backend = backend if backend is not None else CudaWccBackend(graph, **cfg)
+        self.n = self.backend.n
+        self.vb, self.ve = vertex_ranges(self.n, self.world)[self.rank]
+        self.timing = {}
+
+    def _merge_all(self, parent):
+        """All-gather the P forests and link every other rank's tree edges into ours."""
+        b = self.backend
+        if self.world == 1:
+            return
+        gathered = torch.empty((self.world, self.n), dtype=parent.dtype, device=parent.device)
+        dist.all_gather_into_tensor(gathered.view(-1), parent, group=self.group)
+        for q in range(self.world):
+            if q != self.rank:
+                b.phase(_capi.WCC_MERGE, parent, other=gathered[q])
+        b.phase(_capi.WCC_COMPRESS, parent)
+
+    def run(self):
+        b = self.backend
+        parent = b.new_parent()
+        b.phase(_capi.WCC_INIT, parent)
+        b.phase(_capi.WCC_SAMPLE, parent, self.vb, self.ve)
+        b.phase(_capi.WCC_COMPRESS, parent)
+        self._merge_all(parent)
+        label, found = b.sample_label(parent)   # same forest, same seed: the same label on every rank
+        b.phase(_capi.WCC_LINK_REMAINING, parent, self.vb, self.ve, label, found)
+        b.phase(_capi.WCC_COMPRESS, parent)
+        self._merge_all(parent)
+        return parent

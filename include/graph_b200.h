@@ -217,6 +217,31 @@ gb_status gb_page_rank_csr_u32(int device, uint32_t node_count, const uint32_t* 
 gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* components);
 gb_status gb_wcc_device(const gb_graph* graph, const gb_wcc_config* config, uint32_t* d_components);
 
+/* Multi-GPU WCC (1-D cut by vertex range, one process per GPU; the caller owns the exchange of the
+ * parent arrays, e.g. an NCCL all-gather).  The phases of wcc() (wcc.rs:158-183) restricted to the rank's
+ * vertices [vertex_begin, vertex_end) over a FULL parent[n] on every rank:
+ *   INIT, SAMPLE (own vertices), COMPRESS, exchange + MERGE of every other rank's forest, COMPRESS,
+ *   gb_wcc_sample_label on the merged forest (identical on every rank), LINK_REMAINING (own vertices,
+ *   skipping the GLOBAL giant component: skipping a vertex is only safe when the other endpoint of each
+ *   of its edges is either in the same component already or processed by its own owner — which a
+ *   rank-local giant component would not guarantee), COMPRESS, exchange + MERGE, COMPRESS.
+ * The link rule is Afforest::union (afforest.rs:22-39) throughout, so the labels are the minimum node id
+ * of each component on every rank, bit-equal to gb_wcc. */
+typedef enum gb_wcc_phase {
+  GB_WCC_INIT = 0,
+  GB_WCC_SAMPLE = 1,
+  GB_WCC_COMPRESS = 2,
+  GB_WCC_MERGE = 3,
+  GB_WCC_LINK_REMAINING = 4
+} gb_wcc_phase;
+gb_status gb_wcc_shard_phase(const gb_graph* graph, const gb_wcc_config* config, uint32_t phase,
+                             uint32_t vertex_begin, uint32_t vertex_end, uint32_t skip_label, int use_skip,
+                             uint32_t* d_parent, const uint32_t* d_other, void* cuda_stream);
+/* most frequent parent[] among config->sampling_size pseudo-random vertices (find_largest_component,
+ * wcc.rs:245-271; fixed seed); *found = 0 when sampling_size == 0 */
+gb_status gb_wcc_sample_label(const gb_graph* graph, const gb_wcc_config* config, const uint32_t* d_parent,
+                              uint32_t* label, int* found, void* cuda_stream);
+
 /* delta_stepping(&graph, config) -> Vec<AtomicF32>          sssp.rs:38-102
  * distances: node_count floats; unreachable = FLT_MAX (sssp.rs:12). */
 gb_status gb_sssp(const gb_graph* graph, const gb_sssp_config* config, float* distances);

@@ -63,3 +63,40 @@ def test_sharded_page_rank_matches_oracle(exchange):
         assert np.max(np.abs(scores - want) / want) <= 1e-6
         assert abs(err - werr) <= 2e-6
     assert np.max(np.abs(out[0][2] - single) / single) <= 1e-6
+
+
+def _wcc_worker(rank, world, port, scale, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import graph_b200 as gb
+        from graph_b200.multigpu import ShardedWcc
+        gb.set_device(rank)
+        g = gb.DiGraph.rmat(scale, seed=42, layout=gb.Layout.Sorted)
+        comp = ShardedWcc(g).run().cpu().numpy().view(np.uint32)
+        single = g.wcc().components()
+        q.put((rank, bool((comp == single).all()), int(len(np.unique(comp)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_wcc_bit_equal_to_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scale, world = 20, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_wcc_worker, args=(r, world, port, scale, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in got) and len({c for _, _, c in got}) == 1

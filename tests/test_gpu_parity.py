@@ -501,6 +501,41 @@ def test_shard_api_virtual_ranks_match_single_gpu(gb, world):
     assert abs(total - want.error) <= 1e-7 + 1e-6 * want.error
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_wcc_shard_phases_virtual_ranks_bit_exact(gb, world):
+    """Multi-GPU WCC on one GPU: every virtual rank runs the phases on its vertex range over its own
+    full parent array; the all-gather is a list of tensors.  Labels must equal the single-GPU run."""
+    from graph_b200 import _capi
+    from graph_b200.multigpu import CudaWccBackend, vertex_ranges
+    g = gb.DiGraph.rmat(16, seed=3, layout=gb.Layout.Sorted)
+    want = g.wcc().components()
+    b = CudaWccBackend(g)
+    ranges = vertex_ranges(g.node_count(), world)
+    parents = [b.new_parent() for _ in range(world)]
+
+    def merge_all():
+        snap = [p.clone() for p in parents]
+        for r, p in enumerate(parents):
+            for q in range(world):
+                if q != r:
+                    b.phase(_capi.WCC_MERGE, p, other=snap[q])
+            b.phase(_capi.WCC_COMPRESS, p)
+
+    for r, p in enumerate(parents):
+        b.phase(_capi.WCC_INIT, p)
+        b.phase(_capi.WCC_SAMPLE, p, *ranges[r])
+        b.phase(_capi.WCC_COMPRESS, p)
+    merge_all()
+    labels = [b.sample_label(p) for p in parents]
+    assert len(set(labels)) == 1                      # same forest, same seed -> same giant component
+    for r, p in enumerate(parents):
+        b.phase(_capi.WCC_LINK_REMAINING, p, *ranges[r], labels[r][0], labels[r][1])
+        b.phase(_capi.WCC_COMPRESS, p)
+    merge_all()
+    for p in parents:
+        assert (p.cpu().numpy().view(np.uint32) == want).all()
+
+
 # ---- column-block layout under stress: tiny blocks / chunks so that segments are cut by chunk and
 # step boundaries, several hot blocks, the fixup path -------------------------------------------------
 @pytest.mark.parametrize("block,chunk,tau", [(1024, 32, 1.0), (4096, 64, 2.0), (2048, 32, 0.5), (32768, 0, 1e9)])

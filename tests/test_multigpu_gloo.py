@@ -116,3 +116,108 @@ def test_owner_of_rows_is_a_cyclic_deal_of_slices():
     o = owner_of_rows(np.arange(32 * 7 + 5), 3)
     assert (o[:32] == 0).all() and (o[32:64] == 1).all() and (o[64:96] == 2).all() and (o[96:128] == 0).all()
     assert o[-1] == (7 % 3)
+
+
+# ---- multi-GPU WCC orchestration (phases + all-gather + merge) with a numpy backend ----------------
+class NumpyWccBackend:
+    """The phases of gb_wcc_shard_phase on the CPU (Afforest link rule, afforest.rs:22-39)."""
+
+    def __init__(self, out_off, out_tgt, in_off, in_tgt, rounds=2, samples=64):
+        self.oo, self.ot, self.io, self.it = out_off.astype(np.int64), out_tgt, in_off.astype(np.int64), in_tgt
+        self.n = len(out_off) - 1
+        self.rounds, self.samples = rounds, samples
+        self.device = torch.device("cpu")
+
+    def new_parent(self):
+        return torch.empty(self.n, dtype=torch.int32)
+
+    @staticmethod
+    def _link(p, u, v):
+        p1, p2 = p[u], p[v]
+        while p1 != p2:
+            hi, lo = max(p1, p2), min(p1, p2)
+            ph = p[hi]
+            if ph == lo:
+                break
+            if ph == hi:
+                p[hi] = lo
+                break
+            p1, p2 = p[p[hi]], p[lo]
+
+    def phase(self, which, parent, vb=0, ve=0, skip=0, use_skip=0, other=None):
+        from graph_b200 import _capi
+        p = parent.numpy()
+        if which == _capi.WCC_INIT:
+            p[:] = np.arange(self.n)
+        elif which == _capi.WCC_SAMPLE:
+            for u in range(vb, ve):
+                for t in self.ot[self.oo[u]:self.oo[u] + min(self.rounds, self.oo[u + 1] - self.oo[u])]:
+                    self._link(p, u, int(t))
+        elif which == _capi.WCC_COMPRESS:
+            for x in range(self.n):
+                while p[x] != p[p[x]]:
+                    p[x] = p[p[x]]
+        elif which == _capi.WCC_MERGE:
+            o = other.numpy()
+            for v in range(self.n):
+                if o[v] != v:
+                    self._link(p, v, int(o[v]))
+        elif which == _capi.WCC_LINK_REMAINING:
+            for u in range(vb, ve):
+                if use_skip and p[u] == skip:
+                    continue
+                for t in self.ot[self.oo[u] + min(self.rounds, self.oo[u + 1] - self.oo[u]):self.oo[u + 1]]:
+                    self._link(p, u, int(t))
+                for t in self.it[self.io[u]:self.io[u + 1]]:
+                    self._link(p, u, int(t))
+
+    def sample_label(self, parent):
+        p = parent.numpy()
+        idx = (np.arange(self.samples, dtype=np.int64) * 2654435761) % self.n
+        vals, counts = np.unique(p[idx], return_counts=True)
+        return int(vals[np.argmax(counts)]), True
+
+
+def _wcc_worker(rank, world, port, scale, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from graph_b200.multigpu import ShardedWcc
+        src, dst = oracle.rmat_edges(scale, seed=9)
+        n = 1 << scale
+        oo, ot = oracle.csr_build(src, dst, n, oracle.OUTGOING, oracle.SORTED)
+        io, it = oracle.csr_build(src, dst, n, oracle.INCOMING, oracle.SORTED)
+        comp = ShardedWcc(backend=NumpyWccBackend(oo, ot, io, it)).run().numpy().astype(np.uint32)
+        q.put((rank, comp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_wcc_two_ranks_gloo():
+    import oracle
+    scale, world = 9, 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_wcc_worker, args=(r, world, port, scale, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get() for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    src, dst = oracle.rmat_edges(scale, seed=9)
+    oo, ot = oracle.csr_build(src, dst, 1 << scale, oracle.OUTGOING, oracle.SORTED)
+    want = oracle.wcc_min_label(oo, ot)
+    assert (got[0] == want).all() and (got[1] == want).all()   # every rank: min node id per component
+
+
+def test_vertex_ranges_cover_and_align():
+    from graph_b200.multigpu import vertex_ranges
+    for n, w in ((1000, 3), (64, 8), (5, 2), (1 << 20, 8)):
+        r = vertex_ranges(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(lo % 32 == 0 or lo == n for lo, _ in r)
