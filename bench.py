@@ -354,7 +354,7 @@ def run_single(args):
 
 # ---------------------------------------------------------------------------------------------
 def run_multi(args):
-    """N > 1: one process per GPU (torchrun), 1-D edge-cut, per-sweep exchange of the out_scores slices."""
+    """N > 1: one process per GPU (torchrun), 1-D edge-cut (32-row slices dealt round-robin), fused exchange."""
     import torch
     import torch.distributed as dist
     import graph_b200 as gb
@@ -384,44 +384,74 @@ def run_multi(args):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     gteps = m * SWEEPS * args.steps / (ms * 1e-3) / 1e9
-    # e2e: ranks come back to the host every step
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        spr.run(SWEEPS, DAMPING)
-        host = spr.scores_host()
-    torch.cuda.synchronize()
-    dist.barrier()
-    e2e_dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_dt = float(e2e_dt.item())
+    stats = spr.backend.stats
+    # untimed verification: the sharded ranks against a single-GPU run of the same graph on rank 0
+    sharded = spr.scores_host()
+    verified, verification = None, None
+    if rank == 0:
+        single = g.page_rank(max_iterations=SWEEPS, tolerance=0.0, damping_factor=DAMPING, mode="jacobi").scores()
+        worst = float(np.max(np.abs(sharded - single) / single))
+        verified = bool(worst <= 1e-6 and np.isfinite(sharded).all())
+        verification = {"max_rel_err_vs_single_gpu": worst, "rtol": 1e-6,
+                        "what": f"all {n} ranks of the {world}-GPU run against a 1-GPU run of the same graph on rank 0 "
+                                "(itself checked against the oracle at this size by tests/test_gpu_parity.py)"}
     if args.diag:
         spr.diag = []
         spr.run(SWEEPS, DAMPING)
         k_ms, x_ms = spr.diag_summary()
-        info = torch.tensor([k_ms, x_ms, float(spr.backend.stats["local_rows"])], device="cuda", dtype=torch.float64)
+        info = torch.tensor([k_ms, x_ms, float(stats["local_rows"]), float(stats["local_edges"])], device="cuda",
+                            dtype=torch.float64)
         allinfo = [torch.zeros_like(info) for _ in range(world)]
         dist.all_gather(allinfo, info)
         if rank == 0:
-            print("diag per rank (kernel ms, exchange+wait ms, rows):", [[round(float(v), 3) for v in t] for t in allinfo],
-                  file=sys.stderr)
+            print("diag per rank (kernel ms, exchange+wait ms, rows, edges):",
+                  [[round(float(v), 3) for v in t] for t in allinfo], file=sys.stderr)
         spr.diag = None
+    # e2e, same meaning as at N = 1: nothing is resident between steps.  Every rank holds the page_rank
+    # inputs (in-CSR + out offsets) in pinned host memory; a step uploads them, builds this rank's shard
+    # layout, runs the sweeps and brings the full score vector back to the host.
+    (out_off, _out_tgt, in_off, in_tgt), keep = host_csr_from_device(g)
+    del _out_tgt
+    del g
+    torch.cuda.empty_cache()
+    e2e_steps = max(3, min(args.steps, 5))
+    step_s = []
+    for i in range(e2e_steps + 1):   # the first step is a warm-up
+        dist.barrier()
+        t0 = time.perf_counter()
+        gh = gb.DiGraph.for_page_rank(in_off, in_tgt, out_off)
+        spr.rebind(gh)
+        spr.run(SWEEPS, DAMPING)
+        host = spr.scores_host()
+        del gh
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i:
+            step_s.append(float(dt.item()))
+    e2e_med = float(np.median(step_s))
     if rank == 0:
         peak, peak_src = peaks()
+        ab = algorithmic_bytes(n, m)
         line = {
             "metric": "PageRank GTEPS (edges/sec/iter)", "value": gteps, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {**workload_config(scale, world), "exchange": spr.exchange,
                                             "multicast": spr.multicast, "deal": "32-row slices round-robin",
-                                            "layout_rank0": spr.backend.stats},
+                                            "layout_rank0": stats},
             "clocks": clocks.summary(),
-            "e2e": {"value": m * SWEEPS * e2e_steps / e2e_dt / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 32,
-                    "d2h_bytes_per_step": int(4 * n), "steps": e2e_steps,
-                    "what": "sharded page_rank on resident shards + all ranks' scores copied to the host"},
-            "gpu_launches": int(spr.launches),
-            "roofline": {"bound": "hbm", "kernel": "k_pr_cb + k_pr_sell + k_pr_finish (one sweep)", "achieved": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
-                         "peak": peak * world, "unit": "GB/s", "frac": algorithmic_bytes(n, m) * SWEEPS * args.steps / (ms * 1e-3) / 1e9 / (peak * world),
+            "e2e": {"value": m * SWEEPS / e2e_med / 1e9, "unit": "GTEPS",
+                    "h2d_bytes_per_step": int(4 * m + 8 * (n + 1)) * world, "d2h_bytes_per_step": int(4 * n) * world,
+                    "steps": e2e_steps, "ms_per_step": e2e_med * 1e3,
+                    "ms_per_step_all": [round(t * 1e3, 1) for t in step_s],
+                    "what": "per step and per rank: pinned host in-CSR + out offsets -> device, this rank's shard "
+                            "layout, 20 sweeps with the fused exchange, all ranks' scores summed and copied to the "
+                            "host; nothing resident between steps (every rank uploads the whole in-CSR: the storage "
+                            "is not sharded on the host side); median step, max over ranks"},
+            "gpu_launches": int(spr.launches), "verified": verified, "verification": verification,
+            "roofline": {"bound": "hbm", "kernel": "k_pr_cb + k_pr_sell + k_pr_finish + k_pr_sync (one sweep, per rank)",
+                         "achieved": ab * SWEEPS * args.steps / (ms * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": ab * SWEEPS * args.steps / (ms * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs, whole step incl. exchange"},
             "cpu_baseline": None,
         }

@@ -372,6 +372,24 @@ class DiGraph(_Handle):
         return DiGraph(out, micros)
 
     @staticmethod
+    def for_page_rank(in_offsets, in_targets, out_offsets) -> "DiGraph":
+        """Device twin holding only what page_rank reads: the in-CSR and the out-degrees (as out offsets).
+        Arrays are used as given (pass pinned uint32 arrays to upload at PCIe speed)."""
+        io, it, oo = (np.asarray(a) for a in (in_offsets, in_targets, out_offsets))
+        for a in (io, it, oo):
+            if a.dtype != np.uint32 or not a.flags.c_contiguous:
+                raise TypeError("for_page_rank needs contiguous uint32 arrays")
+        _check_host_csr(io, it, "in")
+        if len(oo) != len(io):
+            raise ValueError("in and out offsets must have the same length (node_count + 1)")
+        out = C.c_void_p()
+
+        def go():
+            check(lib.gb_digraph_for_page_rank_u32(_device, len(io) - 1, _ptr(io), _ptr(it), _ptr(oo), C.byref(out)))
+        _, micros = _timed(go)
+        return DiGraph(out, micros)
+
+    @staticmethod
     def rmat(scale: int, edge_factor: int = 16, seed: int = 42, layout=Layout.Sorted, weights=False) -> "DiGraph":
         """Synthetic R-MAT graph generated and built on device (the BASELINE.json workload)."""
         out = C.c_void_p()

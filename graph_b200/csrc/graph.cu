@@ -644,8 +644,10 @@ gb_status gb_graph_copy_csr(const gb_graph* g, gb_csr_which which, uint32_t* off
   DeviceGuard guard(g->device);
   std::lock_guard<std::mutex> lock(g->mu);
   GB_CUDA(cudaMemcpyAsync(off, c->off.p, ((size_t)g->n + 1) * 4, cudaMemcpyDeviceToHost, g->stream));
-  if (tgt && c->len)
+  if (tgt && c->len) {
+    GB_REQUIRE(c->tgt.p != nullptr, "this handle holds no targets for that CSR (page-rank-only twin)");
     GB_CUDA(cudaMemcpyAsync(tgt, c->tgt.p, c->len * 4, cudaMemcpyDeviceToHost, g->stream));
+  }
   if (w) {
     GB_REQUIRE(c->w.p != nullptr, "this CSR carries no edge values");
     if (c->len) GB_CUDA(cudaMemcpyAsync(w, c->w.p, c->len * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -669,6 +671,7 @@ gb_status gb_to_undirected(const gb_graph* dg, gb_layout layout, gb_graph** grap
   if (dg->kind != GB_KIND_DIRECTED) return fail(GB_ERR_UNSUPPORTED, "to_undirected needs a directed graph");
   GB_REQUIRE((int)layout >= 0 && (int)layout <= 2, "bad layout %d", (int)layout);
   uint64_t m = dg->out.len;
+  GB_REQUIRE(m == 0 || dg->out.tgt.p != nullptr, "this handle holds no out targets (page-rank-only twin)");
   GB_REQUIRE(2 * m < 0xFFFFFFFFull, "undirected twin would exceed u32 offsets");
   DeviceGuard guard(dg->device);
   gb_graph* g = nullptr;

@@ -1796,6 +1796,24 @@ gb_status gb_page_rank_csr_u32(int device, uint32_t n, const uint32_t* in_off, c
   return st;
 }
 
+gb_status gb_digraph_for_page_rank_u32(int device, uint32_t n, const uint32_t* in_off, const uint32_t* in_tgt,
+                                       const uint32_t* out_off, gb_graph** graph) {
+  GB_REQUIRE(graph != nullptr, "graph is NULL");
+  GB_REQUIRE(n > 0, "node_count must be > 0");
+  GB_REQUIRE(in_off && out_off, "offset arrays are NULL");
+  GB_REQUIRE(in_off[n] == out_off[n], "in and out offsets disagree on the edge count");
+  gb_graph* g = nullptr;
+  GB_TRY(gb::new_graph(device, GB_KIND_DIRECTED, n, &g));
+  gb_status st = gb::upload_host_csr(g->stream, n, in_off, in_tgt, nullptr, &g->in, "in");
+  if (st == GB_OK) st = gb::upload_host_csr(g->stream, n, out_off, nullptr, nullptr, &g->out, "out");
+  if (st != GB_OK) {
+    gb_graph_free(g);
+    return st;
+  }
+  *graph = g;
+  return GB_OK;
+}
+
 gb_status gb_page_rank_device(const gb_graph* graph, const gb_page_rank_config* config, float* d_scores,
                               uint64_t* ran_iterations, double* error) {
   GB_REQUIRE(d_scores != nullptr, "d_scores is NULL");

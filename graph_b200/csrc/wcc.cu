@@ -156,6 +156,7 @@ static gb_status wcc_impl(const gb_graph* g, const gb_wcc_config* cfg, uint32_t*
   GB_REQUIRE(g && cfg, "NULL argument");
   if (g->kind != GB_KIND_DIRECTED)
     return fail(GB_ERR_UNSUPPORTED, "wcc needs a directed graph (wcc.rs:130: DirectedNeighbors)");
+  GB_REQUIRE(g->out.len == 0 || g->out.tgt.p != nullptr, "this handle holds no out targets (page-rank-only twin)");
   DeviceGuard guard(g->device);
   std::lock_guard<std::mutex> lock(g->mu);
   cudaStream_t s = g->stream;
@@ -216,6 +217,7 @@ gb_status gb_wcc_shard_phase(const gb_graph* g, const gb_wcc_config* cfg, uint32
   if (g->kind != GB_KIND_DIRECTED)
     return gb::fail(GB_ERR_UNSUPPORTED, "wcc needs a directed graph (wcc.rs:130: DirectedNeighbors)");
   GB_REQUIRE(vertex_begin <= vertex_end && vertex_end <= g->n, "bad vertex range [%u, %u)", vertex_begin, vertex_end);
+  GB_REQUIRE(g->out.len == 0 || g->out.tgt.p != nullptr, "this handle holds no out targets (page-rank-only twin)");
   gb::DeviceGuard guard(g->device);
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const uint32_t n = g->n, span = vertex_end - vertex_begin;

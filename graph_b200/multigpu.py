@@ -166,6 +166,22 @@ class ShardedPageRank:
     def launches(self) -> int:
         return getattr(self.backend, "launches", 0)
 
+    def rebind(self, graph):
+        """Point the same exchange state (symmetric buffers, control blocks) at a new graph of the same
+        node count: the old shard layout is released, the new graph's shard is built (collective: every
+        rank rebinds).  Used by the end-to-end path, where nothing of a graph stays resident."""
+        if graph.node_count() != self.n:
+            raise ValueError("rebind needs a graph with the same node count")
+        launches = self.launches
+        self.backend = None            # frees the old shard before the new layout is allocated
+        self.backend = CudaShardBackend(graph, self.rank, self.world)
+        self.backend.launches = launches
+        if self.backend.n_active != self.n_active:
+            self.n_active = self.backend.n_active
+            grid = SLICE * self.world
+            self.active_pad = min(self.n_pad, (self.n_active + grid - 1) // grid * grid)
+        return self
+
     def _exchange(self, x_next):
         if self.exchange == "peer":
             return  # the kernels already stored this rank's values into every peer

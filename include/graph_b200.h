@@ -212,6 +212,13 @@ gb_status gb_page_rank_csr_u32(int device, uint32_t node_count, const uint32_t* 
                                const gb_page_rank_config* config, float* scores,
                                uint64_t* ran_iterations, double* error);
 
+/* The same upload as a handle: a device twin holding exactly what page_rank reads (in-CSR + out-degrees;
+ * there are no out targets, so wcc / sssp / to_undirected on it fail with GB_ERR_INVALID or read an empty
+ * out-CSR).  Used by the multi-GPU path, where every rank builds its shard from host arrays. */
+gb_status gb_digraph_for_page_rank_u32(int device, uint32_t node_count, const uint32_t* in_offsets,
+                                       const uint32_t* in_targets, const uint32_t* out_offsets,
+                                       gb_graph** graph);
+
 /* wcc_afforest(&graph, config).to_vec()                    wcc.rs:127-139, afforest.rs:100-114
  * components[v] = root of v = minimum node id of v's weakly connected component. */
 gb_status gb_wcc(const gb_graph* graph, const gb_wcc_config* config, uint32_t* components);
