@@ -39,7 +39,23 @@ gb_status fail(gb_status st, const char* fmt, ...);
     if (!(cond)) return gb::fail(GB_ERR_INVALID, __VA_ARGS__);  \
   } while (0)
 
-// ---- device buffer (RAII, cudaMallocAsync-free: plain cudaMalloc keeps ncu traces simple) -----
+// ---- device buffer (RAII) ------------------------------------------------------------------------
+// Stream-ordered allocations from the device's default memory pool, whose release threshold is raised
+// once so that freed blocks stay cached: the one-shot entry points (gb_page_rank_csr_u32 uploads a CSR,
+// builds a layout and frees everything on every call) then pay for their ~9 GB of cudaMalloc/cudaFree
+// only the first time.  Semantics stay those of cudaMalloc/cudaFree: alloc returns memory usable on
+// any stream at once, release waits for the device before the block goes back to the pool.
+inline void devbuf_pool_setup() {
+  static thread_local int configured_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == configured_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  configured_for = dev;
+}
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -54,7 +70,10 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaDeviceSynchronize();  // like cudaFree: nothing may still be using the block
+      cudaFreeAsync(p, cudaStreamLegacy);
+    }
     p = nullptr;
     n = 0;
   }
@@ -63,11 +82,14 @@ struct DevBuf {
     release();
     size_t bytes = (count + pad) * sizeof(T);
     if (bytes == 0) bytes = sizeof(T);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    devbuf_pool_setup();
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, cudaStreamLegacy);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);  // usable from every stream now
     if (e != cudaSuccess) {
       p = nullptr;
+      cudaGetLastError();
       return fail(e == cudaErrorMemoryAllocation ? GB_ERR_OOM : GB_ERR_CUDA,
-                  "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+                  "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     }
     n = count;
     return GB_OK;

@@ -56,6 +56,7 @@ constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase r
 constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
+constexpr uint32_t CB_ILP = 4;               // 32-edge batches in flight per warp in the layout build
 // chunk flags (bits 24.. of PrChunk.w)
 constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
 
@@ -259,18 +260,29 @@ __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* 
     const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
     uint32_t rem = 0;
-    for (uint32_t i = 0; i < d; i += 32) {
-      const bool valid = i + lane < d;
-      uint32_t j = CB_NONE;
-      if (valid) {
-        const uint32_t s = new_id[in_tgt[b0 + i + lane]];
-        j = hot_of_blk[s / B];
-        if (j != CB_NONE && l >= nrows[j]) j = CB_NONE;
+    // CB_ILP batches of 32 edges per iteration: their dependent loads (target -> internal id -> block
+    // rank -> row prefix) are issued together, so a hub row's single warp is not latency bound
+    for (uint32_t i = 0; i < d; i += 32 * CB_ILP) {
+      uint32_t j[CB_ILP];
+      bool valid[CB_ILP];
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) {
+        const uint32_t k = i + 32 * u + lane;
+        valid[u] = k < d;
+        j[u] = valid[u] ? new_id[in_tgt[b0 + k]] / B : 0u;
       }
-      const bool cb = j != CB_NONE;
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j);
-      if (cb && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(cnt + poff[j] + l, (uint32_t)__popc(peers));
-      rem += __popc(__ballot_sync(0xFFFFFFFFu, valid && !cb));
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) j[u] = valid[u] ? hot_of_blk[j[u]] : CB_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u)
+        if (j[u] != CB_NONE && l >= nrows[j[u]]) j[u] = CB_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) {
+        const bool cb = j[u] != CB_NONE;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j[u]);
+        if (cb && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(cnt + poff[j[u]] + l, (uint32_t)__popc(peers));
+        rem += __popc(__ballot_sync(0xFFFFFFFFu, valid[u] && !cb));
+      }
     }
     if (lane == 0) {
       lens[l] = rem;
@@ -344,34 +356,50 @@ __global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* _
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
     const uint2 meta = slice_meta[l >> 5];
     uint32_t rem = 0;
-    for (uint32_t i = 0; i < d; i += 32) {
-      const bool valid = i + lane < d;
-      uint32_t j = CB_NONE, s = 0;
-      if (valid) {
-        s = new_id[in_tgt[b0 + i + lane]];
-        j = hot_of_blk[s / B];
-        if (j != CB_NONE && l >= nrows[j]) j = CB_NONE;
+    for (uint32_t i = 0; i < d; i += 32 * CB_ILP) {
+      uint32_t j[CB_ILP], src[CB_ILP], e[CB_ILP], g0[CB_ILP], bk[CB_ILP];
+      bool valid[CB_ILP];
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) {
+        const uint32_t k = i + 32 * u + lane;
+        valid[u] = k < d;
+        src[u] = valid[u] ? new_id[in_tgt[b0 + k]] : 0u;
       }
-      const bool cb = j != CB_NONE;
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j);
-      uint32_t e = 0, base = 0;
-      if (cb) {
-        e = poff[j] + l;
-        base = cur[e];
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) j[u] = valid[u] ? hot_of_blk[src[u] / B] : CB_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u)
+        if (j[u] != CB_NONE && l >= nrows[j[u]]) j[u] = CB_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) {
+        e[u] = g0[u] = bk[u] = 0;
+        if (j[u] != CB_NONE) {
+          e[u] = poff[j[u]] + l;
+          g0[u] = goff[e[u]];
+          bk[u] = blk[j[u]];
+        }
       }
-      __syncwarp();
-      if (cb) {
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        ids[(uint64_t)goff[e] * CB_G + base + rank] = (uint16_t)(s - blk[j] * B);
-        if (rank == 0) cur[e] = base + __popc(peers);
+      // the batches are placed one after the other: positions inside a segment follow the CSR order
+#pragma unroll
+      for (uint32_t u = 0; u < CB_ILP; ++u) {
+        const bool cb = j[u] != CB_NONE;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j[u]);
+        uint32_t base = 0;
+        if (cb) base = cur[e[u]];
+        __syncwarp();
+        if (cb) {
+          const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+          ids[(uint64_t)g0[u] * CB_G + base + rank] = (uint16_t)(src[u] - bk[u] * B);
+          if (rank == 0) cur[e[u]] = base + __popc(peers);
+        }
+        __syncwarp();
+        const uint32_t rb = __ballot_sync(0xFFFFFFFFu, valid[u] && !cb);
+        if (valid[u] && !cb) {
+          const uint32_t q = rem + __popc(rb & ((1u << lane) - 1u));
+          sell[((uint64_t)meta.x + (uint64_t)(q / 4) * 32 + (l & 31u)) * 4 + (q % 4)] = src[u];
+        }
+        rem += __popc(rb);
       }
-      __syncwarp();
-      const uint32_t rb = __ballot_sync(0xFFFFFFFFu, valid && !cb);
-      if (valid && !cb) {
-        const uint32_t q = rem + __popc(rb & ((1u << lane) - 1u));
-        sell[((uint64_t)meta.x + (uint64_t)(q / 4) * 32 + (l & 31u)) * 4 + (q % 4)] = s;
-      }
-      rem += __popc(rb);
     }
   }
 }
