@@ -482,6 +482,18 @@ class DiGraph(_Handle):
         _, micros = _timed(go)
         return WccResult(comp, micros)
 
+    def wcc_afforest_dss(self, **kw) -> WccResult:
+        """wcc_afforest_dss(&graph, config) (wcc.rs:144-156), as `Components::component` reports it: the
+        minimum node id of every node's component — the same labels as wcc().  The reference variant
+        differs only in its backing union-find (DisjointSetStruct, dss.rs), whose raw `to_vec()` may hold
+        non-root ancestors that depend on the thread schedule; nothing consumes it (crates/app/src/app.rs:15
+        drops the result), so the device path does not imitate it."""
+        return self.wcc(**kw)
+
+    def wcc_baseline(self, **kw) -> WccResult:
+        """wcc_baseline(&graph, config) (wcc.rs:103-123): union over every out-edge; same component labels."""
+        return self.wcc(**kw)
+
     def delta_stepping(self, *, start_node: int, delta: float) -> SsspResult:
         """delta_stepping(&graph, DeltaSteppingConfig) (sssp.rs:38-102); needs f32 edge values."""
         if start_node < 0:

@@ -77,6 +77,11 @@ def lib():
                                        C.c_uint64, C.c_uint64, C.c_int, _u32p]
         L.orc_wcc_min_label.restype = None
         L.orc_wcc_min_label.argtypes = [_u32p, _u32p, C.c_uint32, _u32p]
+        L.orc_dss_ops.restype = None
+        L.orc_dss_ops.argtypes = [C.c_uint32, _u32p, C.c_uint64, _u32p, _u32p]
+        L.orc_wcc_dss.restype = None
+        L.orc_wcc_dss.argtypes = [_u32p, _u32p, _u32p, _u32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64,
+                                  C.c_uint64, _u32p, _u32p]
         L.orc_sssp_delta_stepping.restype = C.c_int
         L.orc_sssp_delta_stepping.argtypes = [_u32p, _u32p, _f32p, C.c_uint32, C.c_uint64, C.c_float, _f32p]
         L.orc_sssp_bellman_ford.restype = C.c_int
@@ -216,6 +221,34 @@ def wcc_afforest(out_off, out_tgt, in_off, in_tgt, chunk_size=16384, neighbor_ro
     lib().orc_wcc_afforest(out_off, out_tgt, in_off, in_tgt, n, chunk_size, neighbor_rounds,
                            sampling_size, rng_seed, threads, comp)
     return comp[:n]
+
+
+def dss_ops(n: int, pairs):
+    """DisjointSetStruct (dss.rs:38-116): unions in order -> (to_vec parents, find(i) for every i)."""
+    pairs = _u32(np.asarray(pairs, np.uint32).reshape(-1))
+    if len(pairs) == 0:
+        pairs = np.zeros(2, np.uint32)
+        npairs = 0
+    else:
+        npairs = len(pairs) // 2
+    parents, finds = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.uint32)
+    lib().orc_dss_ops(n, pairs, npairs, parents, finds)
+    return parents[:n], finds[:n]
+
+
+def wcc_dss(out_off, out_tgt, in_off, in_tgt, variant="afforest_dss", neighbor_rounds=2, sampling_size=1024,
+            rng_seed=42):
+    """wcc_baseline / wcc_afforest_dss (wcc.rs:103-156) on one thread -> (to_vec(), component(i) for every i)."""
+    out_off, out_tgt, in_off, in_tgt = _u32(out_off), _u32(out_tgt), _u32(in_off), _u32(in_tgt)
+    n = len(out_off) - 1
+    if len(out_tgt) == 0:
+        out_tgt = np.zeros(1, np.uint32)
+    if len(in_tgt) == 0:
+        in_tgt = np.zeros(1, np.uint32)
+    to_vec, comp = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.uint32)
+    lib().orc_wcc_dss(out_off, out_tgt, in_off, in_tgt, n, {"baseline": 0, "afforest_dss": 1}[variant],
+                      neighbor_rounds, sampling_size, rng_seed, to_vec, comp)
+    return to_vec[:n], comp[:n]
 
 
 def wcc_min_label(out_off, out_tgt):

@@ -590,6 +590,97 @@ ORC_API void orc_wcc_afforest(const uint32_t* out_off, const uint32_t* out_tgt,
   free(parent);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* DisjointSetStruct: crates/algos/src/dss.rs:38-116 (single thread)                          */
+/* ------------------------------------------------------------------------------------------ */
+/* find with path halving, dss.rs:76-94: every visited id is pointed at its grand parent */
+static uint32_t dss_find(uint32_t* p, uint32_t id) {
+  uint32_t parent = p[id];
+  while (id != parent) {
+    uint32_t grand = p[parent];
+    if (p[id] == parent) p[id] = grand; /* update_parent(id, parent, grand_parent): CAS, result ignored */
+    id = parent;
+    parent = grand;
+  }
+  return id;
+}
+/* union by min, dss.rs:38-62 */
+static void dss_union(uint32_t* p, uint32_t id1, uint32_t id2) {
+  for (;;) {
+    id1 = dss_find(p, id1);
+    id2 = dss_find(p, id2);
+    if (id1 == id2) return;
+    if (id1 < id2) {
+      uint32_t t = id1;
+      id1 = id2;
+      id2 = t;
+    }
+    if (p[id1] == id1) { /* update_parent(id1, id1, id2) */
+      p[id1] = id2;
+      return;
+    }
+  }
+}
+ORC_API void orc_dss_ops(uint32_t n, const uint32_t* pairs, uint64_t npairs, uint32_t* parents, uint32_t* finds) {
+  /* unions in order, then find(i) for every i (dss.rs tests :183-220); parents = to_vec() BEFORE the finds */
+  for (uint32_t i = 0; i < n; ++i) parents[i] = i;
+  for (uint64_t k = 0; k < npairs; ++k) dss_union(parents, pairs[2 * k], pairs[2 * k + 1]);
+  uint32_t* work = (uint32_t*)malloc((size_t)(n ? n : 1) * 4);
+  memcpy(work, parents, (size_t)n * 4);
+  for (uint32_t i = 0; i < n; ++i) finds[i] = dss_find(work, i);
+  free(work);
+}
+/* wcc_baseline (variant 0, wcc.rs:103-123: union over every out-edge, no compress) and
+ * wcc_afforest_dss (variant 1, wcc.rs:144-156 + wcc() :158-183 with the DSS as union-find), one thread
+ * in id order.  to_vec = the raw parent array the reference's to_vec() returns (dss.rs:158: entries may
+ * be non-root ancestors: path halving does not fully compress); component[i] = find(i) = what
+ * Components::component returns = the minimum node id of i's component. */
+ORC_API void orc_wcc_dss(const uint32_t* out_off, const uint32_t* out_tgt, const uint32_t* in_off,
+                         const uint32_t* in_tgt, uint32_t n, int variant, uint64_t neighbor_rounds,
+                         uint64_t sampling_size, uint64_t rng_seed, uint32_t* to_vec, uint32_t* component) {
+  uint32_t* p = to_vec;
+  for (uint32_t i = 0; i < n; ++i) p[i] = i;
+  if (variant == 0) {
+    for (uint32_t u = 0; u < n; ++u)
+      for (uint64_t e = out_off[u]; e < out_off[u + 1]; ++e) dss_union(p, u, out_tgt[e]);
+  } else {
+    for (uint32_t u = 0; u < n; ++u) { /* sample_subgraph, wcc.rs:186-204 */
+      uint64_t b = out_off[u], e = out_off[u + 1];
+      uint64_t lim = (e - b < neighbor_rounds) ? e : b + neighbor_rounds;
+      for (uint64_t i = b; i < lim; ++i) dss_union(p, u, out_tgt[i]);
+    }
+    for (uint32_t i = 0; i < n; ++i) dss_find(p, i); /* compress, dss.rs:112-116 */
+    uint32_t best = 0;                                /* find_largest_component, wcc.rs:245-271 */
+    if (n > 0 && sampling_size > 0) {
+      uint32_t* samp = (uint32_t*)malloc((size_t)sampling_size * sizeof(uint32_t));
+      uint64_t s = rng_seed;
+      for (uint64_t i = 0; i < sampling_size; ++i) samp[i] = dss_find(p, (uint32_t)(splitmix64(&s) % n));
+      qsort(samp, sampling_size, sizeof(uint32_t), cmp_u32);
+      uint64_t best_cnt = 0, run = 0;
+      for (uint64_t i = 0; i < sampling_size; ++i) {
+        run = (i > 0 && samp[i] == samp[i - 1]) ? run + 1 : 1;
+        if (run > best_cnt) {
+          best_cnt = run;
+          best = samp[i];
+        }
+      }
+      free(samp);
+    }
+    for (uint32_t u = 0; u < n; ++u) { /* link_remaining, wcc.rs:274-301 */
+      if (sampling_size > 0 && dss_find(p, u) == best) continue;
+      uint64_t b = out_off[u], e = out_off[u + 1];
+      if (e - b > neighbor_rounds)
+        for (uint64_t i = b + neighbor_rounds; i < e; ++i) dss_union(p, u, out_tgt[i]);
+      for (uint64_t i = in_off[u]; i < in_off[u + 1]; ++i) dss_union(p, u, in_tgt[i]);
+    }
+    for (uint32_t i = 0; i < n; ++i) dss_find(p, i); /* final compress */
+  }
+  uint32_t* work = (uint32_t*)malloc((size_t)(n ? n : 1) * 4);
+  memcpy(work, p, (size_t)n * 4);
+  for (uint32_t i = 0; i < n; ++i) component[i] = dss_find(work, i);
+  free(work);
+}
+
 /* Independent statement of the result: label = minimum node id of the weakly connected
  * component (the invariant parent[x] <= x of afforest.rs:22-39 plus full compression). */
 ORC_API void orc_wcc_min_label(const uint32_t* out_off, const uint32_t* out_tgt, uint32_t n,

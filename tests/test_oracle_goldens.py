@@ -227,3 +227,40 @@ def test_rmat_stream_is_deterministic_and_in_range():
     import ctypes as C
     ids = np.arange(1024, dtype=np.uint32)
     assert len(np.unique(np.concatenate([s, d]))) > 300
+
+
+# ---- DisjointSetStruct (crates/algos/src/dss.rs) -----------------------------------------------------
+def test_dss_reference_unit_tests():
+    """dss.rs:183-220: test_union and test_union_with_path_halving, literally."""
+    parents, finds = oracle.dss_ops(10, [(9, 7)])
+    assert finds[9] == 7 and finds[7] == 7                                  # dss.rs:187-188
+    for pairs, want in (([(9, 7), (7, 4)], 4), ([(9, 7), (7, 4), (4, 2)], 2), ([(9, 7), (7, 4), (4, 2), (2, 0)], 0)):
+        assert oracle.dss_ops(10, pairs)[1][9] == want                       # dss.rs:189-194
+    chain = [(4, 3), (3, 2), (2, 1), (1, 0), (9, 8), (8, 7), (7, 6), (6, 5)]
+    _, finds = oracle.dss_ops(10, chain)
+    assert finds[4] == 0 and finds[9] == 5                                   # dss.rs:210-211
+    _, finds = oracle.dss_ops(10, chain + [(5, 4)])
+    assert (finds == 0).all()                                                # dss.rs:213-217
+    # doc tests: union(2, 4) -> find(2) == find(4) == 2 (dss.rs:34-36); union(4, 2) -> find(4) == 2 (:73-75)
+    assert oracle.dss_ops(10, [(2, 4)])[1][[2, 4]].tolist() == [2, 2]
+    assert oracle.dss_ops(10, [(4, 2)])[1][4] == 2
+    # test_union_parallel's postconditions (dss.rs:222-263) on one thread
+    pairs = [(i, i + 1) for i in range(500)] + [(i, i + 1) for i in range(501, 999)]
+    _, finds = oracle.dss_ops(1000, pairs)
+    assert (finds[:501] == finds[0]).all() and finds[500] != finds[501] and (finds[501:] == finds[501]).all()
+
+
+@pytest.mark.parametrize("variant", ["baseline", "afforest_dss"])
+def test_wcc_dss_variants_agree_with_afforest(variant):
+    """wcc_baseline / wcc_afforest_dss (wcc.rs:103-156): component(i) is the minimum node id of i's
+    component — the same labels as wcc_afforest(..).to_vec(); the DSS to_vec() itself may hold non-root
+    ancestors (path halving does not fully compress), which is why it is not a result anybody compares."""
+    src, dst = oracle.rmat_edges(12, seed=5)
+    n = 1 << 12
+    oo, ot = oracle.csr_build(src, dst, n, oracle.OUTGOING, oracle.SORTED)
+    io, it = oracle.csr_build(src, dst, n, oracle.INCOMING, oracle.SORTED)
+    to_vec, comp = oracle.wcc_dss(oo, ot, io, it, variant)
+    want = oracle.wcc_min_label(oo, ot)
+    assert (comp == want).all()
+    assert (to_vec <= np.arange(n)).all()            # union by min: parents never point upwards
+    assert (comp[to_vec] == comp).all()              # every stored parent lies in the node's own component
