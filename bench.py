@@ -459,6 +459,134 @@ def run_multi(args):
     dist.destroy_process_group()
 
 
+def run_algo(args):
+    """--algo wcc | tc | sssp: the other three configs of BASELINE.json on one GPU, one JSON line each, in
+    the same shape as the PageRank line (value = device-timed with the graph resident, e2e = through the
+    host-buffer call, roofline against BASELINE.md's algorithmic bytes, cpu_baseline = the oracle port)."""
+    import torch
+    import graph_b200 as gb
+    import oracle
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(0)
+    gb.set_device(0)
+    peak, peak_src = peaks()
+    reps = max(args.steps, 3)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 1)):
+            fn()
+        dev, wall, launches = [], [], 0
+        res = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = fn()
+            wall.append(time.perf_counter() - t0)
+            t = g.last_timing()
+            dev.append(t["total_ms"])
+            launches += t["kernel_launches"]
+        return res, float(np.median(dev)), float(np.median(wall)) * 1e3, launches
+
+    if args.algo == "wcc":
+        scale = args.scale if args.scale != 26 else 24
+        n, m = 1 << scale, EDGE_FACTOR << scale
+        g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
+        with ClockSampler(0) as clocks:
+            res, dev_ms, wall_ms, launches = timed(lambda: g.wcc())
+        byts = 8 * m + 16 * n + 8
+        comp = res.components()
+        oo, ot = g.csr("out")
+        io, it = g.csr("in")
+        cpu = None
+        verified = None
+        if not args.no_cpu:
+            oracle.wcc_afforest(oo, ot, io, it, threads=0)
+            t0 = time.perf_counter()
+            c = oracle.wcc_afforest(oo, ot, io, it, threads=0)
+            dt = time.perf_counter() - t0
+            verified = bool((c == comp).all())
+            cpu = {"value": m / dt / 1e9, "unit": "G edges/s", "cores": oracle.hardware_threads(), "kind": "port",
+                   "sample": f"one wcc_afforest run (after one warm-up) on the same CSR pair, {dt:.2f} s"}
+        line = {"metric": "WCC (Afforest) G edges/s", "value": m / (dev_ms * 1e-3) / 1e9, "unit": "G edges/s",
+                "ms_per_step": dev_ms, "components": int(len(np.unique(comp))),
+                "config": {"workload": f"wcc_afforest, directed RMAT scale-{scale} (n={n}, m={m}), defaults 16384/2/1024"},
+                "e2e": {"value": m / (wall_ms * 1e-3) / 1e9, "unit": "G edges/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 4 * n, "ms_per_step": wall_ms,
+                        "what": "gb_wcc on the resident twin, component ids copied to the host"},
+                "roofline": {"bound": "hbm", "kernel": "k_cc_* (whole run)", "achieved": byts / (dev_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": byts / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": byts,
+                             "note": "Afforest skips most edge lists, so the effective figure can exceed 1"}}
+    elif args.algo == "tc":
+        scale = args.scale if args.scale != 26 else 22
+        n, m = 1 << scale, EDGE_FACTOR << scale
+        g = gb.Graph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted)
+        with ClockSampler(0) as clocks:
+            raw, raw_ms, _, l0 = timed(lambda: g.global_triangle_count())
+            t0 = time.perf_counter()
+            g.make_degree_ordered()
+            relabel_ms = (time.perf_counter() - t0) * 1e3
+            res, dev_ms, wall_ms, launches = timed(lambda: g.global_triangle_count())
+        launches += l0
+        byts = 8 * m + 4 * (n + 1)
+        cpu, verified = None, None
+        if not args.no_cpu:
+            off, tgt = g.csr()
+            t0 = time.perf_counter()
+            c = oracle.triangle_count(off, tgt, threads=0)
+            dt = time.perf_counter() - t0
+            verified = bool(c == res.triangles)
+            cpu = {"value": m / dt / 1e9, "unit": "G edges/s", "cores": oracle.hardware_threads(), "kind": "port",
+                   "sample": f"one global_triangle_count on the same degree-ordered CSR, {dt:.2f} s"}
+        line = {"metric": "triangle count G edges/s (degree-ordered)", "value": m / (dev_ms * 1e-3) / 1e9,
+                "unit": "G edges/s", "ms_per_step": dev_ms, "triangles": int(res.triangles),
+                "triangles_sorted_layout": int(raw.triangles), "ms_sorted_layout": raw_ms, "relabel_ms": relabel_ms,
+                "config": {"workload": f"global_triangle_count, undirected RMAT scale-{scale} (n={n}, 2m={2 * m} entries), "
+                                       "CsrLayout::Sorted, after make_degree_ordered"},
+                "e2e": {"value": m / (wall_ms * 1e-3) / 1e9, "unit": "G edges/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 8, "ms_per_step": wall_ms, "what": "gb_triangle_count on the resident twin"},
+                "roofline": {"bound": "hbm", "kernel": "k_tc", "achieved": byts / (dev_ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": byts / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": byts,
+                             "note": "compulsory bytes only; the kernel is bound by dependent L2 lookups"}}
+    else:
+        scale = args.scale if args.scale != 26 else 22
+        n, m = 1 << scale, EDGE_FACTOR << scale
+        g = gb.DiGraph.rmat(scale, EDGE_FACTOR, SEED, gb.Layout.Sorted, weights=True)
+        off, _ = g.csr("out")
+        start = int(np.argmax(np.diff(off.astype(np.int64))))
+        delta = 0.05
+        with ClockSampler(0) as clocks:
+            res, dev_ms, wall_ms, launches = timed(lambda: g.delta_stepping(start_node=start, delta=delta))
+        d = res.distances()
+        byts = 8 * m + 4 * (n + 1) + 8 * n
+        cpu, verified = None, None
+        if not args.no_cpu:
+            off, tgt = g.csr("out")
+            w = g.out_weights()
+            t0 = time.perf_counter()
+            c = oracle.sssp_delta_stepping(off, tgt, w, start, delta)
+            dt = time.perf_counter() - t0
+            verified = bool(c.tobytes() == d.tobytes())
+            cpu = {"value": m / dt / 1e9, "unit": "G edges/s", "cores": 1, "kind": "port",
+                   "sample": f"one delta_stepping run (single thread) on the same weighted CSR, {dt:.2f} s"}
+        line = {"metric": "delta-stepping SSSP G edges/s", "value": m / (dev_ms * 1e-3) / 1e9, "unit": "G edges/s",
+                "ms_per_step": dev_ms, "reached": int((d < np.finfo(np.float32).max).sum()),
+                "config": {"workload": f"delta_stepping, weighted RMAT scale-{scale} (n={n}, m={m}), delta {delta}, "
+                                       "start = max out-degree vertex"},
+                "e2e": {"value": m / (wall_ms * 1e-3) / 1e9, "unit": "G edges/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 4 * n, "ms_per_step": wall_ms,
+                        "what": "gb_sssp on the resident twin, distances copied to the host"},
+                "roofline": {"bound": "hbm", "kernel": "k_sssp_* (whole run)", "achieved": byts / (dev_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": byts / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": byts,
+                             "note": "frontier driven: one launch per pass of a bucket"}}
+    line.update({"algo": args.algo, "n_gpus": 1, "steps": reps, "warmup": max(args.warmup, 1), "higher_is_better": True,
+                 "scaling": "strong", "vs_baseline": None, "dtype": "u32" if args.algo != "sssp" else "f32",
+                 "data": "synthetic", "clocks": clocks.summary(), "gpu_launches": int(launches),
+                 "verified": verified, "cpu_baseline": cpu})
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,6 +594,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scale", type=int, default=26)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="page_rank", choices=["page_rank", "wcc", "tc", "sssp"],
+                    help="page_rank = the headline line; wcc / tc / sssp = the other BASELINE.json configs (1 GPU)")
     ap.add_argument("--cpu-sweeps", type=int, default=3, help="sweeps of the CPU baseline sample")
     ap.add_argument("--ref-sweeps", type=int, default=5, help="sweeps per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
@@ -475,6 +605,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.algo != "page_rank":
+        run_algo(args)
     elif args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_multi(args)
     else:
