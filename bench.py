@@ -167,15 +167,18 @@ def verify_last_sweep(g, d_scores, in_off, in_tgt, out_off, n, samples=4096, rto
                         "from a 19-sweep run's out_scores"}
 
 
-def host_csr_from_device(g, pinned=True):
-    """(out_off, out_tgt, in_off, in_tgt) host copies of a DiGraph's CSR pair, pinned when possible."""
+def host_csr_from_device(g, pinned=True, out_targets=True):
+    """(out_off, out_tgt, in_off, in_tgt) host copies of a DiGraph's CSR pair, pinned when possible
+    (out_tgt is None when out_targets is False: page_rank reads only the out-degrees)."""
     from graph_b200._capi import lib, check, CSR_OUT, CSR_IN
     n, m = g.node_count(), g.edge_count()
     keep, arrs = [], []
     for which in (CSR_OUT, CSR_IN):
         t_off, off = pinned_empty(n + 1, np.uint32)
-        t_tgt, tgt = pinned_empty(m, np.uint32)
-        check(lib.gb_graph_copy_csr(g._g, which, off.ctypes.data_as(C.c_void_p), tgt.ctypes.data_as(C.c_void_p), None))
+        want_tgt = out_targets or which == CSR_IN
+        t_tgt, tgt = pinned_empty(m, np.uint32) if want_tgt else (None, None)
+        check(lib.gb_graph_copy_csr(g._g, which, off.ctypes.data_as(C.c_void_p),
+                                    tgt.ctypes.data_as(C.c_void_p) if want_tgt else None, None))
         keep += [t_off, t_tgt]
         arrs += [off, tgt]
     return arrs, keep
@@ -410,8 +413,7 @@ def run_multi(args):
     # e2e, same meaning as at N = 1: nothing is resident between steps.  Every rank holds the page_rank
     # inputs (in-CSR + out offsets) in pinned host memory; a step uploads them, builds this rank's shard
     # layout, runs the sweeps and brings the full score vector back to the host.
-    (out_off, _out_tgt, in_off, in_tgt), keep = host_csr_from_device(g)
-    del _out_tgt
+    (out_off, _none, in_off, in_tgt), keep = host_csr_from_device(g, out_targets=False)
     del g
     torch.cuda.empty_cache()
     e2e_steps = max(3, min(args.steps, 5))
