@@ -54,7 +54,6 @@ constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
 constexpr double CB_TAU_DEFAULT = 2.0;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
 constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
-constexpr uint32_t FIN_TABLE = 1024;          // blocks whose row prefix / partial offset the finish kernel keeps in shared memory
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
 constexpr uint32_t CB_ILP = 4;               // 32-edge batches in flight per warp in the layout build
@@ -618,15 +617,11 @@ __device__ __forceinline__ void cb_chunk_impl(const PrArgs& a, const float* xs, 
   const uint4* ids16 = reinterpret_cast<const uint4*>(a.cb_ids);  // pairs of groups
   const uint4 padv = make_uint4(pad2, pad2, pad2, pad2);
   const uint32_t gs0 = g0 & ~1u;
-  // the id stream is requested THREE steps ahead (DRAM latency ~1 us, a step ~0.15 us of a warp's time:
-  // with one step of lookahead the kernel was bound by the latency of this stream, 32 warps x 512 B in
-  // flight per SM — profiles/r02_prof_v13_s22.summary.txt, long_scoreboard)
-  auto ld_step = [&](uint32_t gs) {
-    return gs + ia < g1 ? ld_stream_u4(reinterpret_cast<const uint32_t*>(ids16 + (gs >> 1) + lane)) : padv;
-  };
-  uint4 ids = ld_step(gs0), ids1 = ld_step(gs0 + 64), ids2 = ld_step(gs0 + 128);
+  uint4 ids = padv;
+  if (gs0 + ia < g1) ids = ld_stream_u4(reinterpret_cast<const uint32_t*>(ids16 + (gs0 >> 1) + lane));
   for (uint32_t gs = gs0; gs < g1; gs += 64) {
-    const uint4 ids3 = ld_step(gs + 192);
+    uint4 nids = padv;
+    if (gs + 64 + ia < g1) nids = ld_stream_u4(reinterpret_cast<const uint32_t*>(ids16 + ((gs + 64) >> 1) + lane));
     // groups outside [g0, g1) belong to the neighbouring chunks
     if (gs + ia < g0) ids.x = ids.y = pad2;
     if (gs + ib >= g1) ids.z = ids.w = pad2;
@@ -668,9 +663,7 @@ __device__ __forceinline__ void cb_chunk_impl(const PrArgs& a, const float* xs, 
     carry = (run_continues && !last_step) ? tl : 0.0;
     if (SPECIAL && W) in_head = false;
     slot0 += __popcll(W);
-    ids = ids1;
-    ids1 = ids2;
-    ids2 = ids3;
+    ids = nids;
   }
 }
 __device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint32_t c, uint32_t lane, uint32_t pad2) {
@@ -868,16 +861,6 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   const uint32_t P = a.deal.P, pp = a.deal.p;
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
   const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
-  // the row prefix and the partial offset of the first FIN_TABLE blocks sit in shared memory: a row's walk
-  // over its blocks then has ONE global load per block (its partial), all of them independent
-  __shared__ uint32_t t_nrows[FIN_TABLE], t_poff[FIN_TABLE];
-  for (uint32_t j = threadIdx.x; j < min(a.KB, FIN_TABLE); j += PR_FIN_THREADS) {
-    t_nrows[j] = __ldg(a.nrows + j);
-    t_poff[j] = __ldg(a.poff + j);
-  }
-  __syncthreads();
-  auto nrows_of = [&](uint32_t j) { return j < FIN_TABLE ? t_nrows[j] : __ldg(a.nrows + j); };
-  auto poff_of = [&](uint32_t j) { return j < FIN_TABLE ? t_poff[j] : __ldg(a.poff + j); };
   // hub rows (segments in more than FIN_CTA_BLOCKS blocks): one CTA per 32-row group — lane = row,
   // warp w adds blocks w, w + 8, ... (independent coalesced loads), warp 0 adds the 8 sums in order
   __shared__ double part[FIN_WARPS][32];
@@ -887,7 +870,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     double s = 0.0;
 #pragma unroll 8
     for (uint32_t j = warp; j < kb; j += FIN_WARPS)
-      if (l < nrows_of(j)) s += (double)a.partial[(size_t)poff_of(j) + l];
+      if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     part[warp][lane] = s;
     __syncthreads();
     if (warp == 0 && l < a.n_cb) {
@@ -925,8 +908,8 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     }
 #pragma unroll 4
     for (uint32_t j = 0; j < kb; ++j) {
-      const uint32_t nr = nrows_of(j);
-      const float* __restrict__ pj = a.partial + poff_of(j);
+      const uint32_t nr = __ldg(a.nrows + j);
+      const float* __restrict__ pj = a.partial + __ldg(a.poff + j);
 #pragma unroll
       for (uint32_t u = 0; u < FIN_U; ++u)
         if (l[u] < nr) s[u] += (double)pj[l[u]];
