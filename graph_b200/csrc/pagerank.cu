@@ -124,6 +124,10 @@ struct PrPlan {
   DevBuf<uint32_t> ctrl;     // [0] = done flag (sweep number at which tolerance was met), [1] = ticket
   size_t smem_cb = 0;
   std::vector<cudaEvent_t> prof_events;
+  // GB_PR_TRACE=1 (diagnostics): CUDA events between the kernels of every sweep; averages are printed
+  // to stderr when the layout is released
+  bool trace = false;
+  mutable std::vector<cudaEvent_t> trace_events;  // 5 per traced sweep
   uint64_t bytes() const {
     return new_id.bytes() + outdeg.bytes() + blk.bytes() + nrows.bytes() + poff.bytes() + cb_ids.bytes() +
            cb_bits.bytes() + partial.bytes() + chunks.bytes() + tail_slot.bytes() + side.bytes() +
@@ -134,6 +138,20 @@ struct PrPlan {
 
 void free_pr_plan(PrPlan* p) {
   if (!p) return;
+  if (p->trace && p->trace_events.size() >= 5) {
+    cudaDeviceSynchronize();
+    double acc[4] = {0, 0, 0, 0};
+    const size_t sweeps = p->trace_events.size() / 5;
+    for (size_t i = 0; i < sweeps; ++i)
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p->trace_events[5 * i + k], p->trace_events[5 * i + k + 1]);
+        acc[k] += ms;
+      }
+    fprintf(stderr, "[gb trace] shard %u/%u, %zu sweeps: k_pr_cb %.4f  k_pr_fixup %.4f  k_pr_sell %.4f  k_pr_finish %.4f ms\n",
+            p->deal.p, p->deal.P, sweeps, acc[0] / sweeps, acc[1] / sweeps, acc[2] / sweeps, acc[3] / sweeps);
+  }
+  for (cudaEvent_t e : p->trace_events) cudaEventDestroy(e);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1300,6 +1318,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     }
     // 7. chunks of the column-block kernel and every persistent CTA's share of them
     p->grid_cb = 0;
+    p->trace = env_u32("GB_PR_TRACE", 0) != 0;
     if (p->NG) {
       // first group of every block's stream
       DevBuf<uint32_t> gbeg;
@@ -1456,15 +1475,33 @@ static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, 
     GB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
     *launches += 2 + (p->n_fix ? 1 : 0);
   } else {
+    cudaEvent_t* ev = nullptr;
+    if (p->trace && p->trace_events.size() < 5 * 256) {
+      const size_t base = p->trace_events.size();
+      p->trace_events.resize(base + 5);
+      for (int k = 0; k < 5; ++k) GB_CUDA(cudaEventCreate(&p->trace_events[base + k]));
+      ev = &p->trace_events[base];
+      GB_CUDA(cudaEventRecord(ev[0], s));
+    }
     if (p->grid_cb) {
       k_pr_cb<<<p->grid_cb, PR_THREADS, p->smem_cb, s>>>(a);
+      if (ev) GB_CUDA(cudaEventRecord(ev[1], s));
       if (p->n_fix) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
       *launches += 1 + (p->n_fix ? 1 : 0);
+    } else if (ev) {
+      GB_CUDA(cudaEventRecord(ev[1], s));
     }
+    if (ev) GB_CUDA(cudaEventRecord(ev[2], s));
     if (p->grid_sell) {
       k_pr_sell<PEERS><<<p->grid_sell, PR_SELL_THREADS, 0, s>>>(a);
       *launches += 1;
     }
+    if (ev) GB_CUDA(cudaEventRecord(ev[3], s));
+    k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+    if (ev) GB_CUDA(cudaEventRecord(ev[4], s));
+    *launches += 1;
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
   }
   k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
   *launches += 1;
