@@ -103,7 +103,7 @@ struct PrPlan {
   DevBuf<double> side;          // [2 n_chunks] head / tail parts of segments cut by chunk boundaries
   DevBuf<uint32_t> fix_list;    // [n_fix] chunks whose tail segment continues in later chunks
   DevBuf<uint2> tasks;          // [n_tasks] chunk ranges of one block each, fattest blocks first
-  DevBuf<uint32_t> task_ctr;    // dynamic task counter (reset by the finish kernel)
+  DevBuf<uint32_t> task_ctr;    // [grid_cb] per-range task cursors (reset by the finish kernel)
   DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
   DevBuf<uint32_t> fin_kb;      // [ceil(n_cb / 32)] blocks of the first row of each 32-row group (finish kernel)
   // SELL-32 (all local active rows; rows < n_cb hold only the edges outside their segments)
@@ -538,7 +538,7 @@ struct PrArgs {
   const uint32_t* fix_list;
   uint32_t n_fix;
   const uint2* tasks;
-  uint32_t n_tasks;
+  uint32_t n_tasks, n_task_ranges;
   uint32_t* task_ctr;
   float* rem;
   // SELL rows
@@ -691,9 +691,12 @@ __device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint3
   else cb_chunk_impl<false>(a, xs, c, ch, lane, pad2);
 }
 
-// Persistent CTAs pull TASKS (up to 64 consecutive chunks of one block) from an atomic counter, fattest
-// blocks first: self-balancing whatever else shares the SM (the SELL kernel in dual mode) and however
-// wrong a cost model of the thin blocks would be (a static split ran 2.4x slower: profiles/r02_*).
+// Persistent CTAs pull TASKS (32 consecutive chunks of one block).  The task list (fattest blocks first)
+// is split into one contiguous RANGE per CTA, each with its own atomic cursor: a CTA first drains its own
+// range — consecutive tasks of one block, so the 192 KB block is loaded once, not once per task — and then
+// steals from the other ranges' cursors.  Self-balancing whatever else shares the SM and however uneven the
+// thin blocks are (a purely static split ran 2.4x slower, one global cursor reloads the block for every
+// task: profiles/r02_sweep_breakdown.txt).
 template <int NT>
 __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   extern __shared__ __align__(16) float smem[];
@@ -703,13 +706,29 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t B = a.B;
   const uint32_t pad2 = B | (B << 16);
+  const uint32_t R = gridDim.x;  // ranges = CTAs
   uint32_t cur_j = CB_NONE;
+  uint32_t r = blockIdx.x, tried = 0;  // range being drained, ranges found empty in a row
   for (;;) {
-    if (threadIdx.x == 0) s_task = atomicAdd(a.task_ctr, 1u);
+    if (threadIdx.x == 0) {
+      uint32_t t = CB_NONE;
+      while (tried < R) {
+        const uint32_t lo = (uint32_t)((uint64_t)a.n_tasks * r / R), hi = (uint32_t)((uint64_t)a.n_tasks * (r + 1) / R);
+        const uint32_t k = lo + atomicAdd(a.task_ctr + r, 1u);
+        if (k < hi) {
+          t = k;
+          tried = 0;
+          break;
+        }
+        r = (r + 1 == R) ? 0 : r + 1;  // this range is drained: try the next one
+        ++tried;
+      }
+      s_task = t;
+    }
     __syncthreads();  // also: every warp is done with the previous task's block
     const uint32_t t = s_task;
     __syncthreads();
-    if (t >= a.n_tasks) break;
+    if (t == CB_NONE) break;
     const uint2 task = a.tasks[t];
     const uint32_t j = a.chunks[task.x].w & 0xFFFFFFu;
     if (j != cur_j) {
@@ -877,7 +896,8 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double err = 0.0;
   const uint32_t P = a.deal.P, pp = a.deal.p;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.task_ctr = 0;  // next sweep's column-block tasks
+  if (blockIdx.x == 0)  // next sweep's column-block task cursors
+    for (uint32_t i = threadIdx.x; i < a.n_task_ranges; i += PR_FIN_THREADS) a.task_ctr[i] = 0;
   const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
   // hub rows (segments in more than FIN_CTA_BLOCKS blocks): one CTA per 32-row group — lane = row,
   // warp w adds blocks w, w + 8, ... (independent coalesced loads), warp 0 adds the 8 sums in order
@@ -1372,8 +1392,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       GB_TRY(p->side.alloc(2));
       GB_TRY(p->tasks.alloc(1));
     }
-    GB_TRY(p->task_ctr.alloc(1));
-    GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
+    GB_TRY(p->task_ctr.alloc(std::max<unsigned>(p->grid_cb, 1)));
+    GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, (size_t)std::max<unsigned>(p->grid_cb, 1) * 4, s));
     GB_TRY(p->partial.alloc(std::max<uint64_t>(p->S, 1)));
     GB_CUDA(cudaMemsetAsync(p->partial.p, 0, std::max<uint64_t>(p->S, 1) * 4, s));
     GB_TRY(p->rem.alloc(std::max<uint32_t>(p->n_cb, 1)));
@@ -1443,6 +1463,7 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.tasks = p->tasks.p;
   a.n_tasks = p->n_tasks;
   a.task_ctr = p->task_ctr.p;
+  a.n_task_ranges = p->grid_cb;
   a.rem = p->rem.p;
   a.fin_kb = p->fin_kb.p;
   a.sell = p->sell.p;
@@ -1548,7 +1569,7 @@ static gb_status run_jacobi(const gb_graph* g, const gb_page_rank_config* cfg, f
   k_pr_init<<<grid_for(n, 256), 256, 0, s>>>(n, p->n_active, init, base, p->deal, p->outdeg.p, p->x[0].p, p->x[1].p,
                                             p->scores.p);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
-  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, (size_t)std::max<unsigned>(p->grid_cb, 1) * 4, s));
   g->timing.kernel_launches += 1;
 
   PrArgs a = make_args(p, base, cfg->damping_factor, cfg->tolerance);
@@ -1715,7 +1736,7 @@ gb_status gb_pr_shard_init(const gb_pr_shard* shard, float damping, float* d_x0,
   gb::k_pr_init<<<gb::grid_for(p->n, 256), 256, 0, s>>>(p->n, p->n_active, init, base, p->deal, p->outdeg.p, d_x0,
                                                        d_x1, d_scores);
   GB_CUDA(cudaMemsetAsync(p->ctrl.p, 0, 8, s));
-  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, 4, s));
+  GB_CUDA(cudaMemsetAsync(p->task_ctr.p, 0, (size_t)std::max<unsigned>(p->grid_cb, 1) * 4, s));
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }
