@@ -708,22 +708,36 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   const uint32_t pad2 = B | (B << 16);
   const uint32_t R = gridDim.x;  // ranges = CTAs
   uint32_t cur_j = CB_NONE;
-  uint32_t r = blockIdx.x, tried = 0;  // range being drained, ranges found empty in a row
+  uint32_t r = blockIdx.x;  // range being drained (warp 0 keeps it)
   for (;;) {
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       uint32_t t = CB_NONE;
-      while (tried < R) {
+      for (;;) {
         const uint32_t lo = (uint32_t)((uint64_t)a.n_tasks * r / R), hi = (uint32_t)((uint64_t)a.n_tasks * (r + 1) / R);
-        const uint32_t k = lo + atomicAdd(a.task_ctr + r, 1u);
-        if (k < hi) {
-          t = k;
-          tried = 0;
-          break;
+        uint32_t k = CB_NONE;
+        if (lane == 0) {
+          k = lo + atomicAdd(a.task_ctr + r, 1u);
+          if (k >= hi) k = CB_NONE;
         }
-        r = (r + 1 == R) ? 0 : r + 1;  // this range is drained: try the next one
-        ++tried;
+        t = __shfl_sync(0xFFFFFFFFu, k, 0);
+        if (t != CB_NONE) break;
+        // this range is drained: the lanes probe the other ranges' cursors 32 at a time (plain loads)
+        uint32_t found = CB_NONE;
+        for (uint32_t base = 1; base < R && found == CB_NONE; base += 32) {
+          uint32_t q = r + base + lane;
+          if (q >= R) q -= R;
+          bool ok = false;
+          if (base + lane < R) {
+            const uint32_t qlo = (uint32_t)((uint64_t)a.n_tasks * q / R), qhi = (uint32_t)((uint64_t)a.n_tasks * (q + 1) / R);
+            ok = *((volatile uint32_t*)(a.task_ctr + q)) < qhi - qlo;
+          }
+          const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+          if (m) found = __shfl_sync(0xFFFFFFFFu, q, __ffs(m) - 1);
+        }
+        if (found == CB_NONE) break;  // every range is drained
+        r = found;
       }
-      s_task = t;
+      if (lane == 0) s_task = t;
     }
     __syncthreads();  // also: every warp is done with the previous task's block
     const uint32_t t = s_task;
