@@ -35,6 +35,49 @@ def set_device(index: int) -> None:
     _device = int(index)
 
 
+class Comm:
+    """Single-process multi-GPU communicator (gb_comm_*): one host thread, N devices, no torch / NCCL.
+
+        comm = Comm([0, 1])
+        graphs = [DiGraph.rmat(22) under set_device(d) for d in comm.devices]   # the same graph on each
+        result = comm.page_rank(graphs, max_iterations=20, tolerance=0.0)
+    """
+
+    def __init__(self, devices):
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self._c = C.c_void_p()
+        check(lib.gb_comm_init(len(self.devices), arr, C.byref(self._c)))
+
+    def __del__(self):
+        c, self._c = getattr(self, "_c", None), None
+        if c:
+            try:
+                lib.gb_comm_free(c)
+            except Exception:
+                pass
+
+    @property
+    def multicast(self) -> bool:
+        n, mc = C.c_int(0), C.c_int(0)
+        check(lib.gb_comm_info(self._c, C.byref(n), C.byref(mc)))
+        return bool(mc.value)
+
+    def page_rank(self, graphs, *, max_iterations: int = 20, tolerance: float = 1e-4, damping_factor: float = 0.85):
+        """page_rank over the communicator's devices (JACOBI schedule); graphs[i] must live on devices[i]."""
+        if len(graphs) != len(self.devices):
+            raise ValueError("one graph per device of the communicator")
+        cfg = _capi.PageRankConfig(int(max_iterations), float(tolerance), float(damping_factor), _capi.PR_JACOBI)
+        arr = (C.c_void_p * len(graphs))(*[g._g for g in graphs])
+        scores = np.empty(graphs[0].node_count(), np.float32)
+        it, err = C.c_uint64(0), C.c_double(0.0)
+
+        def go():
+            check(lib.gb_page_rank_multi(self._c, arr, C.byref(cfg), _ptr(scores), C.byref(it), C.byref(err)))
+        _, micros = _timed(go)
+        return PageRankResult(scores, int(it.value), float(err.value), micros)
+
+
 # ---- enums (crates/mate/src/graphs/mod.rs Layout / FileFormat; csr.rs:35-45) --------------------
 class _Enum:
     def __init__(self, cls_name: str, name: str, value: int):

@@ -108,6 +108,11 @@ SIGNATURES = {
     "gb_pr_shard_sync": (C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, C.c_uint32, _P]),
     "gb_pr_shard_finish": (C.c_int, [_P, _P, _P, _P]),
     "gb_pr_shard_free": (C.c_int, [_P]),
+    "gb_comm_init": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "gb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gb_comm_free": (C.c_int, [_P]),
+    "gb_page_rank_multi": (C.c_int, [_P, _P, C.POINTER(PageRankConfig), _P, C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_double)]),
 }
 
 

@@ -325,6 +325,21 @@ gb_status gb_pr_shard_finish(const gb_pr_shard* shard, const float* d_scores_int
                              float* d_scores_out, void* cuda_stream);
 gb_status gb_pr_shard_free(gb_pr_shard* shard);
 
+/* ---- single-process multi-GPU PageRank ------------------------------------------------------------
+ * For a host that owns N devices itself (the reference is one process): no torch, no NCCL.
+ * gb_comm_init enables peer access all-to-all among `devices` (NULL = 0..ndev-1).  gb_page_rank_multi
+ * takes the SAME graph resident on every device of the communicator (graphs[i] on devices[i]; a
+ * gb_digraph_for_page_rank_u32 twin is enough), builds every device's shard, runs the sweeps with the fused
+ * exchange (one multimem.st per value when the driver offers multicast objects, else one peer store per
+ * device) and the device-side barrier, and returns page_rank's triple (page_rank.rs:58-111).  One host
+ * thread drives all devices; inside the sweep loop the host never waits unless tolerance > 0. */
+typedef struct gb_comm gb_comm;
+gb_status gb_comm_init(int ndev, const int* devices, gb_comm** comm);
+gb_status gb_comm_info(const gb_comm* comm, int* ndev, int* multicast);
+gb_status gb_comm_free(gb_comm* comm);
+gb_status gb_page_rank_multi(gb_comm* comm, const gb_graph* const* graphs, const gb_page_rank_config* config,
+                             float* scores, uint64_t* ran_iterations, double* error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,33 @@ def test_sharded_wcc_bit_equal_to_single_gpu():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in got) and len({c for _, _, c in got}) == 1
+
+
+def test_single_process_communicator_two_gpus():
+    """gb_comm_* / gb_page_rank_multi: one host thread drives both devices (no torch.distributed, no
+    NCCL); ranks <= 1e-6 of the oracle and of a 1-GPU run, also with early stopping."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import oracle
+    import graph_b200 as gb
+    scale = 16
+    graphs = []
+    for d in (0, 1):
+        gb.set_device(d)
+        graphs.append(gb.DiGraph.rmat(scale, seed=42, layout=gb.Layout.Sorted))
+    gb.set_device(0)
+    comm = gb.Comm([0, 1])
+    src, dst = oracle.rmat_edges(scale, seed=42)
+    n = 1 << scale
+    out_off, _ = oracle.csr_build(src, dst, n, oracle.OUTGOING, oracle.SORTED)
+    in_off, in_tgt = oracle.csr_build(src, dst, n, oracle.INCOMING, oracle.SORTED)
+    for maxit, tol in ((20, 0.0), (60, 1e-5)):
+        want, wit, werr = oracle.page_rank_jacobi(in_off, in_tgt, out_off, maxit, tol, 0.85, acc64=True)
+        for _ in range(2):      # a second call reuses the communicator's buffers and sequence numbers
+            pr = comm.page_rank(graphs, max_iterations=maxit, tolerance=tol)
+            assert pr.ran_iterations == wit
+            assert np.max(np.abs(pr.scores() - want) / want) <= 1e-6
+            assert abs(pr.error - werr) <= 2e-6
+    single = graphs[0].page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores()
+    multi = comm.page_rank(graphs, max_iterations=20, tolerance=0.0).scores()
+    assert np.max(np.abs(multi - single) / single) <= 1e-6

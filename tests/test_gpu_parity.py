@@ -536,6 +536,20 @@ def test_wcc_shard_phases_virtual_ranks_bit_exact(gb, world):
         assert (p.cpu().numpy().view(np.uint32) == want).all()
 
 
+def test_single_device_communicator(gb, rmat16):
+    """gb_comm_* with one device: the same entry point a multi-GPU host uses, no peers."""
+    src, dst, n, out, inc = rmat16
+    g = gb.DiGraph.from_csr(out[0], out[1], inc[0], inc[1])
+    comm = gb.Comm([0])
+    assert comm.multicast is False
+    want, it, err = oracle.page_rank_jacobi(inc[0], inc[1], out[0], 20, 0.0, 0.85)
+    pr = comm.page_rank([g], max_iterations=20, tolerance=0.0)
+    assert pr.ran_iterations == 20 and np.max(np.abs(pr.scores() - want) / want) <= PR_RTOL
+    assert abs(pr.error - err) <= ERR_ATOL
+    with pytest.raises(ValueError):
+        comm.page_rank([g, g])
+
+
 # ---- column-block layout under stress: tiny blocks / chunks so that segments are cut by chunk and
 # step boundaries, several hot blocks, the fixup path -------------------------------------------------
 @pytest.mark.parametrize("block,chunk,tau", [(1024, 32, 1.0), (4096, 64, 2.0), (2048, 32, 0.5), (32768, 0, 1e9)])
