@@ -54,6 +54,7 @@ constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
 constexpr double CB_TAU_DEFAULT = 2.0;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
 constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
+constexpr uint32_t SELL_FEW = 4;             // rows with segments in at most this many blocks are finished by k_pr_sell itself
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
 constexpr uint32_t CB_ILP = 4;               // 32-edge batches in flight per warp in the layout build
@@ -114,7 +115,9 @@ struct PrPlan {
   DevBuf<float> x[2];
   DevBuf<float> scores;
   unsigned grid_cb = 0, grid_sell = 0, grid_fin = 1;
-  uint32_t n_fin_warp = 0;   // rows [0, n_fin_warp) own segments in more than 32 blocks
+  uint32_t n_fin_warp = 0;   // rows [0, n_fin_warp) own segments in more than FIN_CTA_BLOCKS blocks
+  uint32_t n_fin = 0;        // rows [0, n_fin) are completed by k_pr_finish, [n_fin, n_cb) by k_pr_sell
+  uint32_t few_nrows[SELL_FEW] = {0, 0, 0, 0}, few_poff[SELL_FEW] = {0, 0, 0, 0};
   // dual mode: k_pr_cb and k_pr_sell run at the same time on the same SMs (two streams, 512-thread CTAs)
   bool dual = false;
   cudaStream_t s2 = nullptr;
@@ -522,6 +525,10 @@ struct PrArgs {
   PrDeal deal;
   uint32_t n_loc, n_cb;
   uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in many blocks (finish: one CTA per 32 rows)
+  uint32_t n_fin;       // rows [0, n_fin) are completed by k_pr_finish (rem[] + partials); rows [n_fin, n_cb) own
+                        // segments in at most SELL_FEW blocks and are completed by their k_pr_sell lane
+  uint32_t few_kb, few_nrows[SELL_FEW], few_poff[SELL_FEW];  // the first blocks' row prefixes / partial offsets
+  uint32_t fix_in_sell; // k_pr_sell adds the parts of cut segments first (sequential mode: no k_pr_fixup launch)
   const uint32_t* fin_kb;  // [ceil(n_cb / 32)] blocks in which the first row of each 32-row group owns a segment
   // column blocks
   uint32_t B, KB;
@@ -773,26 +780,26 @@ __global__ void __maxnreg__(56) k_pr_cb_half(const PrArgs a) { pr_cb_body<PR_THR
 
 // Segments cut by chunk boundaries (segments longer than a chunk): one warp per segment adds its parts
 // in a fixed order — the head part of the first chunk, then lanes over the following chunks (a fixed
-// xor tree per batch of 32).  Tiny; runs after k_pr_cb.
+// xor tree per batch of 32).  Tiny; runs after k_pr_cb (as k_pr_fixup, or as the prologue of k_pr_sell).
+__device__ __forceinline__ void cb_fix_segment(const PrArgs& a, uint32_t c0, uint32_t lane) {
+  double t = a.side[2 * (size_t)c0 + 1];
+  for (uint32_t k0 = c0 + 1;; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    // the walk ends at the first chunk that is not entirely inside the segment (sentinel chunk after the last)
+    const uint32_t fl = a.chunks[min(k, a.n_chunks)].w >> 24;
+    const bool inside = k < a.n_chunks && (fl & CB_INTERIOR) && (fl & CB_TAIL_CONT);
+    const uint32_t stop = __ballot_sync(0xFFFFFFFFu, !inside);
+    const uint32_t upto = stop ? (uint32_t)__ffs(stop) - 1 : 31u;  // last lane that contributes
+    t += warp_sum(lane <= upto ? a.side[2 * (size_t)k] : 0.0);
+    if (stop) break;
+  }
+  if (lane == 0) a.partial[a.tail_slot[c0]] = (float)t;
+}
 __global__ void k_pr_fixup(const PrArgs a) {
   if (a.ctrl[0] != 0) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = gw; i < a.n_fix; i += nw) {
-    const uint32_t c0 = a.fix_list[i];
-    double t = a.side[2 * (size_t)c0 + 1];
-    for (uint32_t k0 = c0 + 1;; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      // the walk ends at the first chunk that is not entirely inside the segment (sentinel chunk after the last)
-      const uint32_t fl = a.chunks[min(k, a.n_chunks)].w >> 24;
-      const bool inside = k < a.n_chunks && (fl & CB_INTERIOR) && (fl & CB_TAIL_CONT);
-      const uint32_t stop = __ballot_sync(0xFFFFFFFFu, !inside);
-      const uint32_t upto = stop ? (uint32_t)__ffs(stop) - 1 : 31u;  // last lane that contributes
-      t += warp_sum(lane <= upto ? a.side[2 * (size_t)k] : 0.0);
-      if (stop) break;
-    }
-    if (lane == 0) a.partial[a.tail_slot[c0]] = (float)t;
-  }
+  for (uint32_t i = gw; i < a.n_fix; i += nw) cb_fix_segment(a, a.fix_list[i], lane);
 }
 
 // ---- SELL-32 sweep: one lane per row ------------------------------------------------------------
@@ -809,6 +816,11 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
   __shared__ double warp_err[NW];
   if (a.ctrl[0] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.fix_in_sell) {
+    // segments cut by chunk boundaries (hub rows only: they are completed by k_pr_finish, after this kernel)
+    const uint32_t gw0 = blockIdx.x * NW + warp, nw0 = gridDim.x * NW;
+    for (uint32_t i = gw0; i < a.n_fix; i += nw0) cb_fix_segment(a, a.fix_list[i], lane);
+  }
   const float* __restrict__ x = a.x_cur;
   double err = 0.0;
   const uint32_t stride = gridDim.x * NW;
@@ -827,7 +839,7 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
     if (0 < meta.y) ta = pr_ld4(base);
     if (1 < meta.y) tb = pr_ld4(base + 32);
     const uint32_t l = 32 * sidx + lane;
-    if (l >= a.n_cb && l < a.n_loc) {
+    if (l >= a.n_fin && l < a.n_loc) {
       const uint32_t gr = deal_global(l, P, pp);
       old = a.scores[gr];
       deg = a.outdeg[gr];
@@ -848,12 +860,20 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
       if (0 < nmeta.y) nta = pr_ld4(nbase);
       if (1 < nmeta.y) ntb = pr_ld4(nbase + 32);
       const uint32_t nl = 32 * nidx + lane;
-      if (nl >= a.n_cb && nl < a.n_loc) {
+      if (nl >= a.n_fin && nl < a.n_loc) {
         const uint32_t ngr = deal_global(nl, P, pp);
         nold = a.scores[ngr];
         ndeg = a.outdeg[ngr];
       }
       if (nidx + stride < a.num_slices) nnmeta = __ldg(a.slice_meta + nidx + stride);
+    }
+    // a row with segments in at most SELL_FEW blocks is completed here: its partials (written by k_pr_cb,
+    // which ran before) are requested now and added after the gathers, in block order like k_pr_finish
+    float part[SELL_FEW];
+#pragma unroll
+    for (uint32_t j = 0; j < SELL_FEW; ++j) {
+      part[j] = 0.0f;
+      if (l >= a.n_fin && j < a.few_kb && l < a.few_nrows[j]) part[j] = a.partial[(size_t)a.few_poff[j] + l];
     }
     float acc = 0.0f;
     for (uint32_t q = 0; q < w4; q += 2) {
@@ -866,8 +886,18 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
       ta = na;
       tb = nb;
     }
-    if (l < a.n_cb) a.rem[l] = acc;
-    else if (l < a.n_loc) err += pr_update<PEERS>(deal_global(l, P, pp), acc, old, deg, a);
+    if (l < a.n_fin) {
+      a.rem[l] = acc;
+    } else if (l < a.n_loc) {
+      if (l < a.n_cb) {
+        double sum = (double)acc;
+#pragma unroll
+        for (uint32_t j = 0; j < SELL_FEW; ++j)
+          if (j < a.few_kb && l < a.few_nrows[j]) sum += (double)part[j];
+        acc = (float)sum;
+      }
+      err += pr_update<PEERS>(deal_global(l, P, pp), acc, old, deg, a);
+    }
     sidx = nidx;
     meta = nmeta;
     nmeta = nnmeta;
@@ -925,7 +955,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
       if (l < __ldg(a.nrows + j)) s += (double)a.partial[(size_t)__ldg(a.poff + j) + l];
     part[warp][lane] = s;
     __syncthreads();
-    if (warp == 0 && l < a.n_cb) {
+    if (warp == 0 && l < a.n_fin) {
       double t = (double)a.rem[l];
 #pragma unroll
       for (int w = 0; w < FIN_WARPS; ++w) t += part[w][lane];
@@ -937,7 +967,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   // all other rows with segments: one lane per row, FIN_U consecutive 32-row groups per warp iteration
   // (the loads of the groups are independent: the walk is latency bound, not bandwidth bound)
   constexpr uint32_t FIN_U = 4;
-  const uint32_t tail_groups = (a.n_cb - a.n_fin_warp + 31) / 32;
+  const uint32_t tail_groups = (a.n_fin - a.n_fin_warp + 31) / 32;
   for (uint32_t w = gw * FIN_U; w < tail_groups; w += nw * FIN_U) {
     const uint32_t l0 = a.n_fin_warp + 32 * w;
     const uint32_t kb = __ldg(a.fin_kb + (l0 >> 5));  // blocks of the first row (it has the most)
@@ -951,7 +981,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
       deg[u] = 1;
       old[u] = 0.0f;
       s[u] = 0.0;
-      if (l[u] < a.n_cb) {
+      if (l[u] < a.n_fin) {
         gr[u] = deal_global(l[u], P, pp);
         old[u] = a.scores[gr[u]];
         deg[u] = a.outdeg[gr[u]];
@@ -968,7 +998,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     }
 #pragma unroll
     for (uint32_t u = 0; u < FIN_U; ++u)
-      if (l[u] < a.n_cb) err += pr_update<PEERS>(gr[u], (float)s[u], old[u], deg[u], a);
+      if (l[u] < a.n_fin) err += pr_update<PEERS>(gr[u], (float)s[u], old[u], deg[u], a);
   }
   err = warp_sum(err);
   if (lane == 0) warp_err[warp] = err;
@@ -1431,8 +1461,15 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     }
     const uint64_t want_sell = ((uint64_t)p->num_slices + PR_SELL_THREADS / 32 - 1) / (PR_SELL_THREADS / 32);
     p->grid_sell = (unsigned)std::min<uint64_t>(want_sell, (uint64_t)dev_sms * 2);
-    p->n_fin_warp = p->KB > FIN_CTA_BLOCKS ? std::min<uint32_t>(p->n_cb, (h_nrows[FIN_CTA_BLOCKS] + 31) / 32 * 32) : 0;
-    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_cb - p->n_fin_warp + 127) / 128;
+    // rows with segments in more than SELL_FEW blocks are a prefix (nrows[] is non-increasing): k_pr_finish
+    // completes them; all others are completed by their k_pr_sell lane (sequential mode: k_pr_cb is done by then)
+    p->n_fin = p->dual ? p->n_cb : (p->KB > SELL_FEW ? std::min<uint32_t>(p->n_cb, (h_nrows[SELL_FEW] + 31) / 32 * 32) : 0);
+    for (uint32_t j = 0; j < SELL_FEW && j < p->KB; ++j) {
+      p->few_nrows[j] = h_nrows[j];
+      p->few_poff[j] = h_poff[j];
+    }
+    p->n_fin_warp = p->KB > FIN_CTA_BLOCKS ? std::min<uint32_t>(p->n_fin, (h_nrows[FIN_CTA_BLOCKS] + 31) / 32 * 32) : 0;
+    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_fin - p->n_fin_warp + 127) / 128;
     const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
     const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
@@ -1460,6 +1497,13 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.n_loc = p->n_loc;
   a.n_cb = p->n_cb;
   a.n_fin_warp = p->n_fin_warp;
+  a.n_fin = p->n_fin;
+  a.few_kb = std::min<uint32_t>(p->KB, SELL_FEW);
+  for (uint32_t j = 0; j < SELL_FEW; ++j) {
+    a.few_nrows[j] = p->few_nrows[j];
+    a.few_poff[j] = p->few_poff[j];
+  }
+  a.fix_in_sell = (!p->dual && p->n_fix && p->grid_sell) ? 1u : 0u;
   a.B = p->B;
   a.KB = p->KB;
   a.blk = p->blk.p;
@@ -1521,8 +1565,8 @@ static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, 
     if (p->grid_cb) {
       k_pr_cb<<<p->grid_cb, PR_THREADS, p->smem_cb, s>>>(a);
       if (ev) GB_CUDA(cudaEventRecord(ev[1], s));
-      if (p->n_fix) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
-      *launches += 1 + (p->n_fix ? 1 : 0);
+      if (p->n_fix && !a.fix_in_sell) k_pr_fixup<<<fix_grid, 128, 0, s>>>(a);
+      *launches += 1 + (p->n_fix && !a.fix_in_sell ? 1 : 0);
     } else if (ev) {
       GB_CUDA(cudaEventRecord(ev[1], s));
     }
@@ -1848,7 +1892,8 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
   stats->tasks = p->n_tasks;
   stats->cut_segments = p->n_fix;
   stats->chunk_groups = p->chunk_groups;
-  stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) + (p->grid_cb && p->n_fix ? 1 : 0);
+  stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) +
+                              (p->grid_cb && p->n_fix && (p->dual || !p->grid_sell) ? 1 : 0);
   stats->device_bytes = p->bytes();
   return GB_OK;
 }
