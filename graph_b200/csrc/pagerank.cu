@@ -51,7 +51,7 @@ constexpr uint32_t PR_MAX_PROFILE_EVENTS = 256;  // sweeps bracketed by CUDA eve
 constexpr uint32_t CB_G = 4;                 // block-local ids per group (one 64-bit load per lane)
 constexpr uint32_t CB_BLOCK_DEFAULT = 49152; // source-vector entries per block (192 KB of shared memory)
 constexpr uint32_t CB_BLOCK_MAX = 56 * 1024;
-constexpr double CB_TAU_DEFAULT = 2.0;       // a (row, block) pair gets a segment if it expects >= tau edges
+constexpr double CB_TAU_DEFAULT = 1.5;       // a (row, block) pair gets a segment if it expects >= tau edges
 constexpr uint32_t CB_MAX_BLOCKS = 8192;     // hot blocks kept (the staircase rarely needs more than ~1000)
 constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
 constexpr uint32_t SELL_FEW = 4;             // rows with segments in at most this many blocks are finished by k_pr_sell itself
