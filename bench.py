@@ -364,6 +364,10 @@ def run_multi(args):
     from graph_b200.multigpu import ShardedPageRank
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # NCCL prints its version banner on stdout: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     gb.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -457,7 +461,8 @@ def run_multi(args):
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs, whole step incl. exchange"},
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     dist.destroy_process_group()
 
 

@@ -22,5 +22,5 @@ for rep in range(2):
     for sw in range(1, a.sweeps + 1):
         b.step(0.85, sw, x[(sw - 1) & 1], x[sw & 1], None, scores, err)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print({"scale": a.scale, "world": a.world, "ms_per_sweep_wall": dt / a.sweeps * 1e3, "stats": b.stats})
+print({"scale": a.scale, "world": a.world, "ms_per_sweep_wall": round(dt / a.sweeps * 1e3, 4), "knobs": {k: v for k, v in os.environ.items() if k.startswith("GB_PR_") and k != "GB_PR_TRACE"}, "tasks": b.stats["tasks"], "chunk_groups": b.stats["chunk_groups"], "hot_blocks": b.stats["hot_blocks"]})
 del b   # prints the trace
