@@ -57,7 +57,6 @@ constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
 constexpr uint32_t SELL_FEW = 4;             // rows with segments in at most this many blocks are finished by k_pr_sell itself
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
-constexpr uint32_t CB_WARP_ROW_DEG = 96;     // layout build: longer rows get a warp, shorter ones a thread
 constexpr uint32_t CB_ILP = 4;               // 32-edge batches in flight per warp in the layout build
 // chunk flags (bits 24.. of PrChunk.w)
 constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
@@ -274,7 +273,6 @@ __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* 
                            const uint32_t* __restrict__ poff, uint32_t B, uint32_t n_cb, PrDeal deal,
                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ lens,
                            unsigned long long* __restrict__ cb_edges) {
-  // n_cb here = the rows that get a warp of their own (a prefix: the long rows)
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -313,57 +311,6 @@ __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* 
     }
   }
   if (lane == 0 && in_cb) atomicAdd(cb_edges, in_cb);
-}
-// the same classification for the short rows [row0, n_cb): one thread per row (a warp per row would idle
-// most of its lanes, and a thread owns its row's pairs outright: plain increments, no match / atomics)
-__global__ void k_cb_count_thread(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                                  const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
-                                  const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
-                                  const uint32_t* __restrict__ poff, uint32_t B, uint32_t row0, uint32_t n_cb,
-                                  PrDeal deal, uint32_t* __restrict__ cnt, uint32_t* __restrict__ lens,
-                                  unsigned long long* __restrict__ cb_edges) {
-  unsigned long long in_cb = 0;
-  for (uint32_t l = row0 + blockIdx.x * blockDim.x + threadIdx.x; l < n_cb; l += gridDim.x * blockDim.x) {
-    const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
-    const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
-    uint32_t rem = 0;
-    for (uint32_t i = 0; i < d; ++i) {
-      const uint32_t j = hot_of_blk[new_id[in_tgt[b0 + i]] / B];
-      if (j != CB_NONE && l < nrows[j]) cnt[poff[j] + l] += 1;
-      else ++rem;
-    }
-    lens[l] = rem;
-    in_cb += d - rem;
-  }
-  for (int o = 16; o > 0; o >>= 1) in_cb += __shfl_xor_sync(0xFFFFFFFFu, in_cb, o);
-  if ((threadIdx.x & 31) == 0 && in_cb) atomicAdd(cb_edges, in_cb);
-}
-__global__ void k_cb_fill_thread(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                                 const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
-                                 const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
-                                 const uint32_t* __restrict__ poff, const uint32_t* __restrict__ blk, uint32_t B,
-                                 uint32_t row0, uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff,
-                                 uint32_t* __restrict__ cur, uint16_t* __restrict__ ids,
-                                 const uint2* __restrict__ slice_meta, uint32_t* __restrict__ sell) {
-  for (uint32_t l = row0 + blockIdx.x * blockDim.x + threadIdx.x; l < n_cb; l += gridDim.x * blockDim.x) {
-    const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
-    const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
-    const uint2 meta = slice_meta[l >> 5];
-    uint32_t rem = 0;
-    for (uint32_t i = 0; i < d; ++i) {  // CSR order: positions inside a segment are deterministic
-      const uint32_t src = new_id[in_tgt[b0 + i]];
-      const uint32_t j = hot_of_blk[src / B];
-      if (j != CB_NONE && l < nrows[j]) {
-        const uint32_t e = poff[j] + l;
-        const uint32_t pos = cur[e];
-        cur[e] = pos + 1;
-        ids[(uint64_t)goff[e] * CB_G + pos] = (uint16_t)(src - blk[j] * B);
-      } else {
-        sell[((uint64_t)meta.x + (uint64_t)(rem / 4) * 32 + (l & 31u)) * 4 + (rem % 4)] = src;
-        ++rem;
-      }
-    }
-  }
 }
 __global__ void k_lens_tail(const uint32_t* __restrict__ indeg, uint32_t n_cb, uint32_t n_loc, PrDeal deal,
                             uint32_t* __restrict__ lens) {
@@ -1289,15 +1236,14 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     // 3. hot blocks: block b carries the share e_b / m of all gathers; a row of in-degree d expects
     //    d * e_b / m edges from it, and gets a segment when that is at least tau
     const uint32_t nblk = (uint32_t)(((uint64_t)n + B - 1) / B);
-    uint32_t n_warp_rows = 0;  // local rows with more than CB_WARP_ROW_DEG in-edges (a prefix): one warp each in the build
     std::vector<uint32_t> h_hot(nblk, CB_NONE), h_blk, h_nrows, h_poff;
     if (p->n_loc && m) {
       DevBuf<unsigned long long> blk_edges, deg_prefix, edges_ge;
       DevBuf<uint32_t> dmin, rows_ge;
       GB_TRY(blk_edges.alloc(nblk));
-      GB_TRY(dmin.alloc(nblk + 1));   // + one probe: rows long enough for a warp of their own in the build
-      GB_TRY(rows_ge.alloc(nblk + 1));
-      GB_TRY(edges_ge.alloc(nblk + 1));
+      GB_TRY(dmin.alloc(nblk));
+      GB_TRY(rows_ge.alloc(nblk));
+      GB_TRY(edges_ge.alloc(nblk));
       GB_TRY(deg_prefix.alloc(std::max<uint32_t>(p->n_active, 1)));
       {
         cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(indeg.p, U32ToU64());
@@ -1312,22 +1258,20 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<unsigned long long> h_edges(nblk);
       GB_CUDA(cudaMemcpyAsync(h_edges.data(), blk_edges.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      std::vector<uint32_t> h_dmin(nblk + 1, 0xFFFFFFFFu);
-      h_dmin[nblk] = CB_WARP_ROW_DEG + 1;
+      std::vector<uint32_t> h_dmin(nblk, 0xFFFFFFFFu);
       for (uint32_t b = 0; b < nblk; ++b)
         if (h_edges[b]) {
           const double d = std::ceil(tau * (double)m / (double)h_edges[b]);
           h_dmin[b] = d >= 4294967295.0 ? 0xFFFFFFFFu : std::max<uint32_t>(1u, (uint32_t)d);
         }
-      GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)(nblk + 1) * 4, cudaMemcpyHostToDevice, s));
-      k_rows_ge<<<grid_for(nblk + 1, 128), 128, 0, s>>>(indeg.p, deg_prefix.p, p->n_active, dmin.p, nblk + 1, rows_ge.p,
-                                                         edges_ge.p);
-      std::vector<uint32_t> h_rows(nblk + 1);
-      std::vector<unsigned long long> h_ege(nblk + 1);
-      GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)(nblk + 1) * 4, cudaMemcpyDeviceToHost, s));
-      GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)nblk * 4, cudaMemcpyHostToDevice, s));
+      k_rows_ge<<<grid_for(nblk, 128), 128, 0, s>>>(indeg.p, deg_prefix.p, p->n_active, dmin.p, nblk, rows_ge.p,
+                                                     edges_ge.p);
+      std::vector<uint32_t> h_rows(nblk);
+      std::vector<unsigned long long> h_ege(nblk);
+      GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      n_warp_rows = deal_count(h_rows[nblk], deal.P, deal.p);
       // GB_PR_MIN_BLOCK (experiment): drop blocks whose segments are expected to hold fewer ids than this
       // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers).
       // Default 0: a thin block costs one 128 KB load (~2 us on one SM), while its ids would otherwise
@@ -1371,15 +1315,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     GB_TRY(goff.alloc(p->S + 1));
     GB_CUDA(cudaMemsetAsync(goff.p, 0, (p->S + 1) * 4, s));
     GB_TRY(lens.alloc(std::max<uint32_t>(p->n_loc, 1)));
-    n_warp_rows = std::min(n_warp_rows, p->n_cb);
-    if (n_warp_rows)
-      k_cb_count<<<grid_for((uint64_t)n_warp_rows * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, n_warp_rows, deal,
+    if (p->n_cb)
+      k_cb_count<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, p->n_cb, deal,
           goff.p, lens.p, counters.p + 2);
-    if (p->n_cb > n_warp_rows)
-      k_cb_count_thread<<<grid_for(p->n_cb - n_warp_rows, 128), 128, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, n_warp_rows, p->n_cb,
-          deal, goff.p, lens.p, counters.p + 2);
     if (p->n_loc > p->n_cb)
       k_lens_tail<<<grid_for(p->n_loc - p->n_cb, 256), 256, 0, s>>>(indeg.p, p->n_cb, p->n_loc, deal, lens.p);
     if (p->S) {
@@ -1428,16 +1367,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       DevBuf<uint32_t> cur;
       GB_TRY(cur.alloc(p->S));
       GB_CUDA(cudaMemsetAsync(cur.p, 0, p->S * 4, s));
-      if (n_warp_rows)
-        k_cb_fill<<<grid_for((uint64_t)n_warp_rows * 32, 256), 256, 0, s>>>(
-            g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B,
-            n_warp_rows, deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
-            reinterpret_cast<uint32_t*>(p->sell.p));
-      if (p->n_cb > n_warp_rows)
-        k_cb_fill_thread<<<grid_for(p->n_cb - n_warp_rows, 128), 128, 0, s>>>(
-            g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B,
-            n_warp_rows, p->n_cb, deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
-            reinterpret_cast<uint32_t*>(p->sell.p));
+      k_cb_fill<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, p->n_cb,
+          deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
+          reinterpret_cast<uint32_t*>(p->sell.p));
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
