@@ -57,6 +57,8 @@ constexpr uint32_t CB_TASK_CHUNKS = 32;      // chunks per task (one per warp)
 constexpr uint32_t SELL_FEW = 4;             // rows with segments in at most this many blocks are finished by k_pr_sell itself
 constexpr uint32_t FIN_CTA_BLOCKS = 64;      // finish: 32-row groups with segments in more blocks get a CTA each
 constexpr uint32_t CB_NONE = 0xFFFFFFFFu;
+constexpr uint32_t CB_MEGA_DEG = 32768;      // layout build: rows with more in-edges go through one stable radix sort
+constexpr uint32_t CB_MEGA_JBITS = 14;       // key = row << 14 | block rank (0x3FFF = not in a segment)
 constexpr uint32_t CB_ILP = 4;               // 32-edge batches in flight per warp in the layout build
 // chunk flags (bits 24.. of PrChunk.w)
 constexpr uint32_t CB_HEAD_CONT = 1u, CB_TAIL_CONT = 2u, CB_INTERIOR = 4u;
@@ -270,14 +272,14 @@ struct U32ToU64 {
 __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
                            const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
                            const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
-                           const uint32_t* __restrict__ poff, uint32_t B, uint32_t n_cb, PrDeal deal,
+                           const uint32_t* __restrict__ poff, uint32_t B, uint32_t row0, uint32_t n_cb, PrDeal deal,
                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ lens,
                            unsigned long long* __restrict__ cb_edges) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long in_cb = 0;
-  for (uint32_t l = warp; l < n_cb; l += nwarps) {
+  for (uint32_t l = row0 + warp; l < n_cb; l += nwarps) {
     const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
     uint32_t rem = 0;
@@ -311,6 +313,71 @@ __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* 
     }
   }
   if (lane == 0 && in_cb) atomicAdd(cb_edges, in_cb);
+}
+// ---- the longest rows (a prefix of the local rows) go through ONE stable radix sort -----------------
+// A row's warp walks it 128 edges at a time, ~3 us per step: a million-edge hub would take tens of
+// milliseconds on its own.  Its edges are instead keyed (row << 14 | block rank), sorted stably — so
+// the edges of one (row, block) pair end up contiguous AND in CSR order — and counted / placed from the
+// sorted sequence, one thread per edge.
+__global__ void k_mega_deg(const uint32_t* __restrict__ indeg, uint32_t n_mega, PrDeal deal, uint32_t* __restrict__ out) {
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < n_mega; l += gridDim.x * blockDim.x)
+    out[l] = indeg[deal_global(l, deal.P, deal.p)];
+}
+__global__ void k_mega_keys(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                            const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
+                            const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows, uint32_t B,
+                            const uint32_t* __restrict__ moff, uint32_t n_mega, uint32_t M, PrDeal deal,
+                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = n_mega;  // row with moff[row] <= i < moff[row + 1]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) / 2;
+      if (moff[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    const uint32_t l = lo;
+    const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
+    const uint32_t src = new_id[in_tgt[in_off[old] + (i - moff[l])]];
+    uint32_t j = hot_of_blk[src / B];
+    if (j != CB_NONE && l >= nrows[j]) j = CB_NONE;
+    keys[i] = (l << CB_MEGA_JBITS) | (j == CB_NONE ? (1u << CB_MEGA_JBITS) - 1u : j);
+    vals[i] = src;
+  }
+}
+__global__ void k_mega_starts(const uint32_t* __restrict__ keys, uint32_t M, uint32_t* __restrict__ start) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x)
+    start[i] = (i == 0 || keys[i] != keys[i - 1]) ? i : 0u;  // max-scanned into "first index of my run"
+}
+__global__ void k_mega_counts(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ start, uint32_t M,
+                              const uint32_t* __restrict__ poff, uint32_t* __restrict__ cnt,
+                              uint32_t* __restrict__ lens, unsigned long long* __restrict__ cb_edges) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    if (i + 1 < M && keys[i + 1] == keys[i]) continue;  // not the last edge of its run
+    const uint32_t len = i + 1 - start[i];
+    const uint32_t l = keys[i] >> CB_MEGA_JBITS, j = keys[i] & ((1u << CB_MEGA_JBITS) - 1u);
+    if (j == (1u << CB_MEGA_JBITS) - 1u) {
+      lens[l] = len;
+    } else {
+      cnt[poff[j] + l] = len;
+      atomicAdd(cb_edges, (unsigned long long)len);
+    }
+  }
+}
+__global__ void k_mega_fill(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                            const uint32_t* __restrict__ start, uint32_t M, const uint32_t* __restrict__ poff,
+                            const uint32_t* __restrict__ blk, uint32_t B, const uint32_t* __restrict__ goff,
+                            uint16_t* __restrict__ ids, const uint2* __restrict__ slice_meta,
+                            uint32_t* __restrict__ sell) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    const uint32_t pos = i - start[i];
+    const uint32_t l = keys[i] >> CB_MEGA_JBITS, j = keys[i] & ((1u << CB_MEGA_JBITS) - 1u);
+    if (j == (1u << CB_MEGA_JBITS) - 1u) {
+      const uint2 meta = slice_meta[l >> 5];
+      sell[((uint64_t)meta.x + (uint64_t)(pos / 4) * 32 + (l & 31u)) * 4 + (pos % 4)] = vals[i];
+    } else {
+      ids[(uint64_t)goff[poff[j] + l] * CB_G + pos] = (uint16_t)(vals[i] - blk[j] * B);
+    }
+  }
 }
 __global__ void k_lens_tail(const uint32_t* __restrict__ indeg, uint32_t n_cb, uint32_t n_loc, PrDeal deal,
                             uint32_t* __restrict__ lens) {
@@ -366,13 +433,13 @@ __global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* _
                           const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
                           const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
                           const uint32_t* __restrict__ poff, const uint32_t* __restrict__ blk, uint32_t B,
-                          uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff, uint32_t* __restrict__ cur,
-                          uint16_t* __restrict__ ids, const uint2* __restrict__ slice_meta,
+                          uint32_t row0, uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff,
+                          uint32_t* __restrict__ cur, uint16_t* __restrict__ ids, const uint2* __restrict__ slice_meta,
                           uint32_t* __restrict__ sell) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t l = warp; l < n_cb; l += nwarps) {
+  for (uint32_t l = row0 + warp; l < n_cb; l += nwarps) {
     const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
     const uint2 meta = slice_meta[l >> 5];
@@ -1236,14 +1303,15 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     // 3. hot blocks: block b carries the share e_b / m of all gathers; a row of in-degree d expects
     //    d * e_b / m edges from it, and gets a segment when that is at least tau
     const uint32_t nblk = (uint32_t)(((uint64_t)n + B - 1) / B);
+    uint32_t n_mega = 0;  // local rows [0, n_mega) are long enough for the sort path of the build
     std::vector<uint32_t> h_hot(nblk, CB_NONE), h_blk, h_nrows, h_poff;
     if (p->n_loc && m) {
       DevBuf<unsigned long long> blk_edges, deg_prefix, edges_ge;
       DevBuf<uint32_t> dmin, rows_ge;
       GB_TRY(blk_edges.alloc(nblk));
-      GB_TRY(dmin.alloc(nblk));
-      GB_TRY(rows_ge.alloc(nblk));
-      GB_TRY(edges_ge.alloc(nblk));
+      GB_TRY(dmin.alloc(nblk + 1));  // + one probe: the rows long enough for the sort path of the build
+      GB_TRY(rows_ge.alloc(nblk + 1));
+      GB_TRY(edges_ge.alloc(nblk + 1));
       GB_TRY(deg_prefix.alloc(std::max<uint32_t>(p->n_active, 1)));
       {
         cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(indeg.p, U32ToU64());
@@ -1258,20 +1326,22 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       std::vector<unsigned long long> h_edges(nblk);
       GB_CUDA(cudaMemcpyAsync(h_edges.data(), blk_edges.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
-      std::vector<uint32_t> h_dmin(nblk, 0xFFFFFFFFu);
+      std::vector<uint32_t> h_dmin(nblk + 1, 0xFFFFFFFFu);
+      h_dmin[nblk] = env_u32("GB_PR_MEGA", CB_MEGA_DEG) + 1;
       for (uint32_t b = 0; b < nblk; ++b)
         if (h_edges[b]) {
           const double d = std::ceil(tau * (double)m / (double)h_edges[b]);
           h_dmin[b] = d >= 4294967295.0 ? 0xFFFFFFFFu : std::max<uint32_t>(1u, (uint32_t)d);
         }
-      GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)nblk * 4, cudaMemcpyHostToDevice, s));
-      k_rows_ge<<<grid_for(nblk, 128), 128, 0, s>>>(indeg.p, deg_prefix.p, p->n_active, dmin.p, nblk, rows_ge.p,
-                                                     edges_ge.p);
-      std::vector<uint32_t> h_rows(nblk);
-      std::vector<unsigned long long> h_ege(nblk);
-      GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, s));
-      GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(dmin.p, h_dmin.data(), (size_t)(nblk + 1) * 4, cudaMemcpyHostToDevice, s));
+      k_rows_ge<<<grid_for(nblk + 1, 128), 128, 0, s>>>(indeg.p, deg_prefix.p, p->n_active, dmin.p, nblk + 1, rows_ge.p,
+                                                         edges_ge.p);
+      std::vector<uint32_t> h_rows(nblk + 1);
+      std::vector<unsigned long long> h_ege(nblk + 1);
+      GB_CUDA(cudaMemcpyAsync(h_rows.data(), rows_ge.p, (size_t)(nblk + 1) * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaMemcpyAsync(h_ege.data(), edges_ge.p, (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
+      n_mega = deal_count(h_rows[nblk], deal.P, deal.p);
       // GB_PR_MIN_BLOCK (experiment): drop blocks whose segments are expected to hold fewer ids than this
       // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers).
       // Default 0: a thin block costs one 128 KB load (~2 us on one SM), while its ids would otherwise
@@ -1315,9 +1385,67 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     GB_TRY(goff.alloc(p->S + 1));
     GB_CUDA(cudaMemsetAsync(goff.p, 0, (p->S + 1) * 4, s));
     GB_TRY(lens.alloc(std::max<uint32_t>(p->n_loc, 1)));
-    if (p->n_cb)
-      k_cb_count<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, p->n_cb, deal,
+    // the longest rows: key, sort, count from the sorted sequence (kept for the fill pass below)
+    n_mega = std::min(n_mega, std::min(p->n_cb, (1u << (32 - CB_MEGA_JBITS)) - 1u));
+    if (p->KB >= (1u << CB_MEGA_JBITS) - 1u) n_mega = 0;
+    DevBuf<uint32_t> mega_keys, mega_vals, mega_start, mega_off;
+    uint32_t M = 0;
+    if (n_mega) {
+      DevBuf<uint32_t> mdeg;
+      GB_TRY(mdeg.alloc(n_mega));
+      k_mega_deg<<<grid_for(n_mega, 128), 128, 0, s>>>(indeg.p, n_mega, deal, mdeg.p);
+      std::vector<uint32_t> h_moff(n_mega + 1, 0);
+      GB_CUDA(cudaMemcpyAsync(h_moff.data() + 1, mdeg.p, (size_t)n_mega * 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      uint64_t acc = 0;
+      for (uint32_t r = 0; r < n_mega; ++r) {
+        acc += h_moff[r + 1];
+        if (acc >= 0xFFFFFFF0ull) {  // more mega edges than a 32-bit sort index holds: shorten the prefix
+          n_mega = r;
+          acc -= h_moff[r + 1];
+          break;
+        }
+        h_moff[r + 1] = (uint32_t)acc;
+      }
+      h_moff.resize(n_mega + 1);
+      M = n_mega ? h_moff[n_mega] : 0;
+      if (M) {
+        GB_TRY(upload(s, &mega_off, h_moff));
+        DevBuf<uint32_t> keys_in, vals_in;
+        GB_TRY(keys_in.alloc(M));
+        GB_TRY(vals_in.alloc(M));
+        GB_TRY(mega_keys.alloc(M));
+        GB_TRY(mega_vals.alloc(M));
+        GB_TRY(mega_start.alloc(M));
+        k_mega_keys<<<grid_for(M, 256), 256, 0, s>>>(g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p,
+                                                     p->nrows.p, B, mega_off.p, n_mega, M, deal, keys_in.p, vals_in.p);
+        uint32_t row_bits = 1;
+        while ((1u << row_bits) < n_mega) ++row_bits;
+        size_t tb = 0;
+        GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
+                                                (int)(CB_MEGA_JBITS + row_bits), s));
+        DevBuf<uint8_t> tmp;
+        GB_TRY(tmp.alloc(tb));
+        GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
+                                                (int)(CB_MEGA_JBITS + row_bits), s));
+        k_mega_starts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, M, mega_start.p);
+        size_t sb = 0;
+        GB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
+        DevBuf<uint8_t> stmp;
+        GB_TRY(stmp.alloc(sb));
+        GB_CUDA(cub::DeviceScan::InclusiveScan(stmp.p, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
+        GB_CUDA(cudaMemsetAsync(lens.p, 0, (size_t)n_mega * 4, s));
+        k_mega_counts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, mega_start.p, M, p->poff.p, goff.p, lens.p,
+                                                       counters.p + 2);
+        GB_CUDA(cudaGetLastError());
+        GB_CUDA(cudaStreamSynchronize(s));  // keys_in / vals_in / tmp / stmp are released here
+      } else {
+        n_mega = 0;
+      }
+    }
+    if (p->n_cb > n_mega)
+      k_cb_count<<<grid_for((uint64_t)(p->n_cb - n_mega) * 32, 256), 256, 0, s>>>(
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, n_mega, p->n_cb, deal,
           goff.p, lens.p, counters.p + 2);
     if (p->n_loc > p->n_cb)
       k_lens_tail<<<grid_for(p->n_loc - p->n_cb, 256), 256, 0, s>>>(indeg.p, p->n_cb, p->n_loc, deal, lens.p);
@@ -1367,10 +1495,15 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       DevBuf<uint32_t> cur;
       GB_TRY(cur.alloc(p->S));
       GB_CUDA(cudaMemsetAsync(cur.p, 0, p->S * 4, s));
-      k_cb_fill<<<grid_for((uint64_t)p->n_cb * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, p->n_cb,
-          deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
-          reinterpret_cast<uint32_t*>(p->sell.p));
+      if (M)
+        k_mega_fill<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, mega_vals.p, mega_start.p, M, p->poff.p, p->blk.p, B,
+                                                     goff.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
+                                                     reinterpret_cast<uint32_t*>(p->sell.p));
+      if (p->n_cb > n_mega)
+        k_cb_fill<<<grid_for((uint64_t)(p->n_cb - n_mega) * 32, 256), 256, 0, s>>>(
+            g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, n_mega,
+            p->n_cb, deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
+            reinterpret_cast<uint32_t*>(p->sell.p));
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
