@@ -17,13 +17,15 @@
 // first); the source vector is cut into blocks of B entries that fit in shared memory, and every
 // (row, block) pair that is expected to hold at least tau edges gets a SEGMENT of 16-bit block-local
 // source ids in that block's stream.  A persistent CTA loads a block into shared memory with 128-bit
-// loads, then its warps stream the segments (coalesced 64-bit loads, 4 ids per lane), gather from
+// loads, then its warps stream the segments (coalesced 128-bit loads, 8 ids per lane), gather from
 // shared memory, and reduce lanes that belong to the same row with a segmented warp scan; one f32
 // partial per (row, block) pair goes back to HBM.  Edges of pairs below the threshold (and all edges
 // of short rows) stay in a SELL-32 layout with 32-bit ids: one lane per row, gathers through L1/L2
-// with the first 32 K sources mirrored in shared memory.  A finish kernel adds each row's partials
-// in a fixed order (f64), applies the update of page_rank.rs:148-158 and reduces the sweep error.
-// Everything is deterministic: bit-identical run to run and for every shard count.
+// (no shared memory: the whole 228 KB serve as L1); that kernel also completes every row whose
+// segments lie in at most 4 blocks.  A finish kernel adds the hub rows' partials in a fixed order
+// (f64), applies the update of page_rank.rs:148-158 and reduces the sweep error.
+// Everything is deterministic: bit-identical run to run for a given shard count; across shard counts the
+// ranks agree to ~2e-7.
 //
 // Multi-GPU (1-D edge-cut by destination): the 32-row slices of the internal order are dealt
 // round-robin to the P ranks, so every rank holds the same mix of hub and tail rows; a rank builds the
@@ -1344,7 +1346,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       n_mega = deal_count(h_rows[nblk], deal.P, deal.p);
       // GB_PR_MIN_BLOCK (experiment): drop blocks whose segments are expected to hold fewer ids than this
       // (this shard's share of: in-edges of the qualifying rows x the block's share of all gathers).
-      // Default 0: a thin block costs one 128 KB load (~2 us on one SM), while its ids would otherwise
+      // Default 0: a thin block costs one block load (~2 us on one SM), while its ids would otherwise
       // lengthen the SELL lanes of the hub rows, which one lane walks serially.
       double min_ids = 0.0;
       if (const char* e = getenv("GB_PR_MIN_BLOCK")) min_ids = atof(e);

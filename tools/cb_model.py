@@ -1,10 +1,10 @@
 """cb_model.py — lane-level numpy model of the column-block kernel's chunk logic (pagerank.cu:
-cb_cut / k_cb_chunks / cb_chunk / the fixup prologue of k_pr_sell).
+cb_cut / k_cb_chunks / cb_chunk_impl / cb_fix_segment).
 
 There is no GPU in the build container, so the trickiest index logic (chunk cuts inside long
 segments, start-bit row counting, the carried run, side buffers and their fixed-order fixup) is
 restated here lane by lane and checked against a direct per-segment sum on random segment lengths.
-Run: python tools/cb_model.py   (also imported by tests/test_cb_model.py)."""
+Run: python tools/cb_model.py   (also exercised by tests/test_cb_model.py)."""
 from __future__ import annotations
 
 import numpy as np
