@@ -56,6 +56,21 @@ inline void devbuf_pool_setup() {
   }
   configured_for = dev;
 }
+// Inside a DevBufStreamScope every buffer released by this thread is known to have been used on that
+// one stream only, so release waits for the stream instead of the device: the layout build can then drop
+// its temporaries while a copy stream is still bringing in the rest of the graph.
+inline cudaStream_t*& devbuf_scope_slot() {
+  static thread_local cudaStream_t* slot = nullptr;
+  return slot;
+}
+struct DevBufStreamScope {
+  cudaStream_t stream;
+  cudaStream_t* prev;
+  explicit DevBufStreamScope(cudaStream_t s) : stream(s), prev(devbuf_scope_slot()) { devbuf_scope_slot() = &stream; }
+  ~DevBufStreamScope() { devbuf_scope_slot() = prev; }
+  DevBufStreamScope(const DevBufStreamScope&) = delete;
+  DevBufStreamScope& operator=(const DevBufStreamScope&) = delete;
+};
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -71,7 +86,9 @@ struct DevBuf {
   ~DevBuf() { release(); }
   void release() {
     if (p) {
-      cudaDeviceSynchronize();  // like cudaFree: nothing may still be using the block
+      // like cudaFree: nothing may still be using the block
+      if (cudaStream_t* scoped = devbuf_scope_slot()) cudaStreamSynchronize(*scoped);
+      else cudaDeviceSynchronize();
       cudaFreeAsync(p, cudaStreamLegacy);
     }
     p = nullptr;
@@ -114,6 +131,17 @@ struct PrPlan;  // pagerank.cu
 }  // namespace gb
 
 // the opaque handle of the C ABI
+namespace gb {
+// Host targets of the in-CSR that are still on their way to the device (gb_page_rank_csr_u32): the copy
+// stream brings them in row-aligned chunks, and the layout build classifies chunk k while chunk k+1 is
+// on the bus.  row_begin[k] .. row_begin[k+1] are the ORIGINAL row ids of chunk k.
+struct TargetFeed {
+  std::vector<uint32_t> row_begin;   // [chunks + 1]
+  std::vector<uint64_t> edge_begin;  // [chunks + 1] = in_off[row_begin[k]]
+  std::vector<cudaEvent_t> ready;    // [chunks] recorded on the copy stream behind each chunk
+};
+}  // namespace gb
+
 struct gb_graph {
   int device = 0;
   gb_graph_kind kind = GB_KIND_DIRECTED;
@@ -124,6 +152,7 @@ struct gb_graph {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   mutable std::mutex mu;            // algorithms on one handle serialise on its stream
   mutable gb::PrPlan* pr_plan = nullptr;  // lazily built PageRank layout (pagerank.cu)
+  mutable const gb::TargetFeed* feed = nullptr;  // set only while gb_page_rank_csr_u32 streams the targets in
   mutable gb_timing timing{};
   uint64_t extra_bytes = 0;
 };

@@ -267,15 +267,76 @@ struct U32ToU64 {
   __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
 };
 
-// One warp per local row that owns segments: classify its in-edges.  An edge from source s (internal
-// id) lands in block s / B; if that block is hot (rank j) and the row is inside the block's row prefix
-// it belongs to segment (j, row), else to the row's SELL remainder.  The same traversal order is
-// used by the fill kernel, so positions inside a segment follow the CSR order: deterministic.
+// Classification of the in-edges of the rows that own segments (local rows [n_mega, n_cb)).  An edge
+// from source s (internal id) lands in block s / B; if that block is hot (rank j) and the row is inside
+// the block's row prefix it belongs to segment (j, row), else to the row's SELL remainder.  One warp walks
+// a row in CSR order and leaves one 8-byte RECORD per edge, so that the fill pass — which has to wait for
+// the scan over all segment sizes — is a plain scatter with no lookups left:
+//   segment edge:   x = block-local id | j << 16,   y = 1 << 31 | position inside the segment
+//   remainder edge: x = internal source id,         y = position inside the row's SELL lane
+// Positions follow the CSR order (the per-pair counter is advanced batch by batch, each batch waits for
+// the previous one's counter value): the layout is deterministic.
+constexpr uint32_t CB_REC_SEG = 0x80000000u;
+template <bool CHECK>
+__device__ __forceinline__ uint32_t cb_classify_row(uint32_t l, uint32_t b0, uint32_t d, uint32_t n,
+                                                    const uint32_t* __restrict__ in_tgt,
+                                                    const uint32_t* __restrict__ new_id,
+                                                    const uint32_t* __restrict__ hot_of_blk,
+                                                    const uint32_t* __restrict__ nrows,
+                                                    const uint32_t* __restrict__ poff,
+                                                    const uint32_t* __restrict__ blk, uint32_t B,
+                                                    uint32_t* __restrict__ cnt, uint2* __restrict__ rec, uint32_t lane) {
+  uint32_t rem = 0;
+  // CB_ILP batches of 32 edges per iteration: their dependent loads (target -> internal id -> block
+  // rank -> row prefix) are issued together, so a long row's single warp is not latency bound
+  for (uint32_t i = 0; i < d; i += 32 * CB_ILP) {
+    uint32_t j[CB_ILP], src[CB_ILP];
+    bool valid[CB_ILP];
+#pragma unroll
+    for (uint32_t u = 0; u < CB_ILP; ++u) {
+      const uint32_t k = i + 32 * u + lane;
+      valid[u] = k < d;
+      src[u] = 0;
+      if (valid[u]) {
+        uint32_t t = in_tgt[b0 + k];
+        if (CHECK && t >= n) t = 0;  // reported by k_feed_check; keep the lookups in range meanwhile
+        src[u] = new_id[t];
+      }
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < CB_ILP; ++u) j[u] = valid[u] ? hot_of_blk[src[u] / B] : CB_NONE;
+#pragma unroll
+    for (uint32_t u = 0; u < CB_ILP; ++u)
+      if (j[u] != CB_NONE && l >= nrows[j[u]]) j[u] = CB_NONE;
+#pragma unroll
+    for (uint32_t u = 0; u < CB_ILP; ++u) {
+      const bool cb = j[u] != CB_NONE;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j[u]);
+      const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+      uint32_t base = 0, local = 0;
+      if (cb) {
+        local = src[u] - blk[j[u]] * B;
+        if (lane == leader) base = atomicAdd(cnt + poff[j[u]] + l, (uint32_t)__popc(peers));
+      }
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);  // also orders this batch's counter update before the next
+      const uint32_t rb = __ballot_sync(0xFFFFFFFFu, valid[u] && !cb);
+      if (cb) {
+        rec[b0 + i + 32 * u + lane] = make_uint2(local | (j[u] << 16), CB_REC_SEG | (base + __popc(peers & ((1u << lane) - 1u))));
+      } else if (valid[u]) {
+        rec[b0 + i + 32 * u + lane] = make_uint2(src[u], rem + __popc(rb & ((1u << lane) - 1u)));
+      }
+      rem += __popc(rb);
+    }
+  }
+  return rem;
+}
+// rows in internal order (the whole in-CSR is resident): one warp per local row
 __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
                            const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
                            const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
-                           const uint32_t* __restrict__ poff, uint32_t B, uint32_t row0, uint32_t n_cb, PrDeal deal,
-                           uint32_t* __restrict__ cnt, uint32_t* __restrict__ lens,
+                           const uint32_t* __restrict__ poff, const uint32_t* __restrict__ blk, uint32_t B,
+                           uint32_t row0, uint32_t n_cb, PrDeal deal, uint32_t* __restrict__ cnt,
+                           uint2* __restrict__ rec, uint32_t* __restrict__ lens,
                            unsigned long long* __restrict__ cb_edges) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -284,37 +345,68 @@ __global__ void k_cb_count(const uint32_t* __restrict__ in_off, const uint32_t* 
   for (uint32_t l = row0 + warp; l < n_cb; l += nwarps) {
     const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
-    uint32_t rem = 0;
-    // CB_ILP batches of 32 edges per iteration: their dependent loads (target -> internal id -> block
-    // rank -> row prefix) are issued together, so a hub row's single warp is not latency bound
-    for (uint32_t i = 0; i < d; i += 32 * CB_ILP) {
-      uint32_t j[CB_ILP];
-      bool valid[CB_ILP];
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u) {
-        const uint32_t k = i + 32 * u + lane;
-        valid[u] = k < d;
-        j[u] = valid[u] ? new_id[in_tgt[b0 + k]] / B : 0u;
-      }
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u) j[u] = valid[u] ? hot_of_blk[j[u]] : CB_NONE;
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u)
-        if (j[u] != CB_NONE && l >= nrows[j[u]]) j[u] = CB_NONE;
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u) {
-        const bool cb = j[u] != CB_NONE;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j[u]);
-        if (cb && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(cnt + poff[j[u]] + l, (uint32_t)__popc(peers));
-        rem += __popc(__ballot_sync(0xFFFFFFFFu, valid[u] && !cb));
-      }
-    }
+    const uint32_t rem = cb_classify_row<false>(l, b0, d, 0u, in_tgt, new_id, hot_of_blk, nrows, poff, blk, B, cnt, rec, lane);
     if (lane == 0) {
       lens[l] = rem;
       in_cb += d - rem;
     }
   }
   if (lane == 0 && in_cb) atomicAdd(cb_edges, in_cb);
+}
+// rows [v0, v1) in ORIGINAL order (a chunk of the in-CSR that has just arrived over PCIe): a warp takes
+// 32 consecutive rows, keeps those that are local and own segments, and walks them one after the other
+__global__ void k_cb_count_rows(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
+                                const uint32_t* __restrict__ new_id, const uint32_t* __restrict__ hot_of_blk,
+                                const uint32_t* __restrict__ nrows, const uint32_t* __restrict__ poff,
+                                const uint32_t* __restrict__ blk, uint32_t B, uint32_t v0, uint32_t v1, uint32_t n,
+                                uint32_t row0, uint32_t n_cb, PrDeal deal, uint32_t* __restrict__ cnt,
+                                uint2* __restrict__ rec, uint32_t* __restrict__ lens,
+                                unsigned long long* __restrict__ cb_edges) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long in_cb = 0;
+  for (uint64_t base = (uint64_t)v0 + 32ull * warp; base < v1; base += 32ull * nwarps) {
+    const uint64_t v = base + lane;
+    uint32_t l = CB_NONE, b0 = 0, d = 0;
+    if (v < v1) {
+      const uint32_t gid = new_id[v], slice = gid >> 5;
+      if (slice % deal.P == deal.p) {
+        const uint32_t loc = ((slice / deal.P) << 5) | (gid & 31u);
+        if (loc >= row0 && loc < n_cb) {
+          l = loc;
+          b0 = in_off[v];
+          d = in_off[v + 1] - b0;
+        }
+      }
+    }
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, l != CB_NONE);
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t rl = __shfl_sync(0xFFFFFFFFu, l, src_lane);
+      const uint32_t rb = __shfl_sync(0xFFFFFFFFu, b0, src_lane);
+      const uint32_t rd = __shfl_sync(0xFFFFFFFFu, d, src_lane);
+      const uint32_t rem = cb_classify_row<true>(rl, rb, rd, n, in_tgt, new_id, hot_of_blk, nrows, poff, blk, B, cnt, rec, lane);
+      if (lane == 0) {
+        lens[rl] = rem;
+        in_cb += rd - rem;
+      }
+    }
+  }
+  if (lane == 0 && in_cb) atomicAdd(cb_edges, in_cb);
+}
+// range check of a chunk of targets and of the offsets of its rows (what validate_device_targets does
+// for a resident CSR)
+__global__ void k_feed_check(const uint32_t* __restrict__ tgt, uint64_t count, uint32_t n, unsigned int* __restrict__ bad) {
+  unsigned int mine = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    mine += tgt[i] >= n;
+  if (mine) atomicAdd(bad, mine);
+}
+__global__ void k_feed_monotone(const uint32_t* __restrict__ off, uint32_t n, unsigned int* __restrict__ bad) {
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    if (off[v] > off[v + 1]) atomicAdd(bad, 1u);
 }
 // ---- the longest rows (a prefix of the local rows) go through ONE stable radix sort -----------------
 // A row's warp walks it 128 edges at a time, ~3 us per step: a million-edge hub would take tens of
@@ -429,15 +521,12 @@ __global__ void k_sell_meta(const uint32_t* __restrict__ units, const uint32_t* 
   for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < num_slices; sidx += gridDim.x * blockDim.x)
     meta[sidx] = make_uint2(bases[sidx], units[sidx] / 32);
 }
-// second traversal of the rows that own segments: block-local ids into the segments (CSR order inside
-// a segment), all other sources into the row's SELL lane
-__global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ in_tgt,
-                          const uint32_t* __restrict__ old_of, const uint32_t* __restrict__ new_id,
-                          const uint32_t* __restrict__ hot_of_blk, const uint32_t* __restrict__ nrows,
-                          const uint32_t* __restrict__ poff, const uint32_t* __restrict__ blk, uint32_t B,
-                          uint32_t row0, uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff,
-                          uint32_t* __restrict__ cur, uint16_t* __restrict__ ids, const uint2* __restrict__ slice_meta,
-                          uint32_t* __restrict__ sell) {
+// after the scan over the segment sizes: scatter the records left by the classification — block-local
+// ids into the segments, all other sources into the row's SELL lane
+__global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ old_of,
+                          const uint2* __restrict__ rec, const uint32_t* __restrict__ poff, uint32_t row0,
+                          uint32_t n_cb, PrDeal deal, const uint32_t* __restrict__ goff, uint16_t* __restrict__ ids,
+                          const uint2* __restrict__ slice_meta, uint32_t* __restrict__ sell) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -445,50 +534,26 @@ __global__ void k_cb_fill(const uint32_t* __restrict__ in_off, const uint32_t* _
     const uint32_t old = old_of[deal_global(l, deal.P, deal.p)];
     const uint32_t b0 = in_off[old], d = in_off[old + 1] - b0;
     const uint2 meta = slice_meta[l >> 5];
-    uint32_t rem = 0;
     for (uint32_t i = 0; i < d; i += 32 * CB_ILP) {
-      uint32_t j[CB_ILP], src[CB_ILP], e[CB_ILP], g0[CB_ILP], bk[CB_ILP];
-      bool valid[CB_ILP];
+      uint2 r[CB_ILP];
+      uint32_t g0[CB_ILP];
 #pragma unroll
       for (uint32_t u = 0; u < CB_ILP; ++u) {
         const uint32_t k = i + 32 * u + lane;
-        valid[u] = k < d;
-        src[u] = valid[u] ? new_id[in_tgt[b0 + k]] : 0u;
+        r[u] = k < d ? rec[b0 + k] : make_uint2(0u, 0xFFFFFFFFu);
       }
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u) j[u] = valid[u] ? hot_of_blk[src[u] / B] : CB_NONE;
 #pragma unroll
       for (uint32_t u = 0; u < CB_ILP; ++u)
-        if (j[u] != CB_NONE && l >= nrows[j[u]]) j[u] = CB_NONE;
+        g0[u] = (r[u].y != 0xFFFFFFFFu && (r[u].y & CB_REC_SEG)) ? goff[poff[r[u].x >> 16] + l] : 0u;
 #pragma unroll
       for (uint32_t u = 0; u < CB_ILP; ++u) {
-        e[u] = g0[u] = bk[u] = 0;
-        if (j[u] != CB_NONE) {
-          e[u] = poff[j[u]] + l;
-          g0[u] = goff[e[u]];
-          bk[u] = blk[j[u]];
+        if (r[u].y == 0xFFFFFFFFu) continue;
+        if (r[u].y & CB_REC_SEG) {
+          ids[(uint64_t)g0[u] * CB_G + (r[u].y & ~CB_REC_SEG)] = (uint16_t)(r[u].x & 0xFFFFu);
+        } else {
+          const uint32_t q = r[u].y;
+          sell[((uint64_t)meta.x + (uint64_t)(q / 4) * 32 + (l & 31u)) * 4 + (q % 4)] = r[u].x;
         }
-      }
-      // the batches are placed one after the other: positions inside a segment follow the CSR order
-#pragma unroll
-      for (uint32_t u = 0; u < CB_ILP; ++u) {
-        const bool cb = j[u] != CB_NONE;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, j[u]);
-        uint32_t base = 0;
-        if (cb) base = cur[e[u]];
-        __syncwarp();
-        if (cb) {
-          const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-          ids[(uint64_t)g0[u] * CB_G + base + rank] = (uint16_t)(src[u] - bk[u] * B);
-          if (rank == 0) cur[e[u]] = base + __popc(peers);
-        }
-        __syncwarp();
-        const uint32_t rb = __ballot_sync(0xFFFFFFFFu, valid[u] && !cb);
-        if (valid[u] && !cb) {
-          const uint32_t q = rem + __popc(rb & ((1u << lane) - 1u));
-          sell[((uint64_t)meta.x + (uint64_t)(q / 4) * 32 + (l & 31u)) * 4 + (q % 4)] = src[u];
-        }
-        rem += __popc(rb);
       }
     }
   }
@@ -1251,6 +1316,10 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
   p->n = n;
   p->m = m;
   p->deal = deal;
+  // every temporary below is used on s only: releasing one waits for s, not for the device (a copy
+  // stream may still be bringing in the targets, see TargetFeed)
+  DevBufStreamScope scope(s);
+  const TargetFeed* feed = g->feed;
   gb_status st = [&]() -> gb_status {
     int dev_sms = 148;
     GB_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
@@ -1411,44 +1480,73 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       }
       h_moff.resize(n_mega + 1);
       M = n_mega ? h_moff[n_mega] : 0;
-      if (M) {
-        GB_TRY(upload(s, &mega_off, h_moff));
-        DevBuf<uint32_t> keys_in, vals_in;
-        GB_TRY(keys_in.alloc(M));
-        GB_TRY(vals_in.alloc(M));
-        GB_TRY(mega_keys.alloc(M));
-        GB_TRY(mega_vals.alloc(M));
-        GB_TRY(mega_start.alloc(M));
-        k_mega_keys<<<grid_for(M, 256), 256, 0, s>>>(g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p,
-                                                     p->nrows.p, B, mega_off.p, n_mega, M, deal, keys_in.p, vals_in.p);
-        uint32_t row_bits = 1;
-        while ((1u << row_bits) < n_mega) ++row_bits;
-        size_t tb = 0;
-        GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
-                                                (int)(CB_MEGA_JBITS + row_bits), s));
-        DevBuf<uint8_t> tmp;
-        GB_TRY(tmp.alloc(tb));
-        GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
-                                                (int)(CB_MEGA_JBITS + row_bits), s));
-        k_mega_starts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, M, mega_start.p);
-        size_t sb = 0;
-        GB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
-        DevBuf<uint8_t> stmp;
-        GB_TRY(stmp.alloc(sb));
-        GB_CUDA(cub::DeviceScan::InclusiveScan(stmp.p, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
-        GB_CUDA(cudaMemsetAsync(lens.p, 0, (size_t)n_mega * 4, s));
-        k_mega_counts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, mega_start.p, M, p->poff.p, goff.p, lens.p,
-                                                       counters.p + 2);
-        GB_CUDA(cudaGetLastError());
-        GB_CUDA(cudaStreamSynchronize(s));  // keys_in / vals_in / tmp / stmp are released here
-      } else {
-        n_mega = 0;
-      }
+      if (M) GB_TRY(upload(s, &mega_off, h_moff));
+      else n_mega = 0;
     }
-    if (p->n_cb > n_mega)
+    // all other rows that own segments: one record per in-edge (consumed by the fill pass)
+    DevBuf<uint2> rec;
+    if (p->n_cb > n_mega) {
+      uint32_t dmax = 0;  // a record holds a 31-bit position
+      GB_CUDA(cudaMemcpyAsync(&dmax, indeg.p + deal_global(n_mega, deal.P, deal.p), 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      GB_REQUIRE(dmax < 0x7FFFFFFFu, "a row with %u in-edges outside the sort path of the layout build", dmax);
+      GB_TRY(rec.alloc(std::max<uint64_t>(m, 1)));
+    }
+    if (feed) {
+      // the targets arrive chunk by chunk: check and classify each chunk as soon as it is there
+      DevBuf<unsigned int> bad;
+      GB_TRY(bad.alloc(1));
+      GB_CUDA(cudaMemsetAsync(bad.p, 0, 4, s));
+      for (size_t k = 0; k + 1 < feed->row_begin.size(); ++k) {
+        const uint32_t v0 = feed->row_begin[k], v1 = feed->row_begin[k + 1];
+        const uint64_t e0 = feed->edge_begin[k], e1 = feed->edge_begin[k + 1];
+        GB_CUDA(cudaStreamWaitEvent(s, feed->ready[k], 0));
+        if (e1 > e0) k_feed_check<<<grid_for(e1 - e0, 256), 256, 0, s>>>(g->in.tgt.p + e0, e1 - e0, n, bad.p);
+        if (p->n_cb > n_mega && v1 > v0)
+          k_cb_count_rows<<<grid_for((uint64_t)(v1 - v0), 256), 256, 0, s>>>(
+              g->in.off.p, g->in.tgt.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, v0, v1, n, n_mega,
+              p->n_cb, deal, goff.p, rec.p, lens.p, counters.p + 2);
+      }
+      unsigned int nbad = 0;
+      GB_CUDA(cudaGetLastError());
+      GB_CUDA(cudaMemcpyAsync(&nbad, bad.p, 4, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      GB_REQUIRE(nbad == 0, "in CSR holds %u targets >= node_count %u", nbad, n);
+    } else if (p->n_cb > n_mega) {
       k_cb_count<<<grid_for((uint64_t)(p->n_cb - n_mega) * 32, 256), 256, 0, s>>>(
-          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, B, n_mega, p->n_cb, deal,
-          goff.p, lens.p, counters.p + 2);
+          g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, n_mega,
+          p->n_cb, deal, goff.p, rec.p, lens.p, counters.p + 2);
+    }
+    if (M) {
+      DevBuf<uint32_t> keys_in, vals_in;
+      GB_TRY(keys_in.alloc(M));
+      GB_TRY(vals_in.alloc(M));
+      GB_TRY(mega_keys.alloc(M));
+      GB_TRY(mega_vals.alloc(M));
+      GB_TRY(mega_start.alloc(M));
+      k_mega_keys<<<grid_for(M, 256), 256, 0, s>>>(g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p,
+                                                   p->nrows.p, B, mega_off.p, n_mega, M, deal, keys_in.p, vals_in.p);
+      uint32_t row_bits = 1;
+      while ((1u << row_bits) < n_mega) ++row_bits;
+      size_t tb = 0;
+      GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
+                                              (int)(CB_MEGA_JBITS + row_bits), s));
+      DevBuf<uint8_t> tmp;
+      GB_TRY(tmp.alloc(tb));
+      GB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.p, mega_keys.p, vals_in.p, mega_vals.p, (int)M, 0,
+                                              (int)(CB_MEGA_JBITS + row_bits), s));
+      k_mega_starts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, M, mega_start.p);
+      size_t sb = 0;
+      GB_CUDA(cub::DeviceScan::InclusiveScan(nullptr, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
+      DevBuf<uint8_t> stmp;
+      GB_TRY(stmp.alloc(sb));
+      GB_CUDA(cub::DeviceScan::InclusiveScan(stmp.p, sb, mega_start.p, mega_start.p, cub::Max(), (int)M, s));
+      GB_CUDA(cudaMemsetAsync(lens.p, 0, (size_t)n_mega * 4, s));
+      k_mega_counts<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, mega_start.p, M, p->poff.p, goff.p, lens.p,
+                                                     counters.p + 2);
+      GB_CUDA(cudaGetLastError());
+      GB_CUDA(cudaStreamSynchronize(s));  // keys_in / vals_in / tmp / stmp are released here
+    }
     if (p->n_loc > p->n_cb)
       k_lens_tail<<<grid_for(p->n_loc - p->n_cb, 256), 256, 0, s>>>(indeg.p, p->n_cb, p->n_loc, deal, lens.p);
     if (p->S) {
@@ -1494,18 +1592,14 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
     if (p->NG) {
       k_fill_u2<<<grid_for(p->NG + 64, 256), 256, 0, s>>>(p->cb_ids.p, p->NG + 64, make_uint2(B | (B << 16), B | (B << 16)));
       k_cb_bits<<<grid_for(p->S, 256), 256, 0, s>>>(goff.p, p->S, p->cb_bits.p);
-      DevBuf<uint32_t> cur;
-      GB_TRY(cur.alloc(p->S));
-      GB_CUDA(cudaMemsetAsync(cur.p, 0, p->S * 4, s));
       if (M)
         k_mega_fill<<<grid_for(M, 256), 256, 0, s>>>(mega_keys.p, mega_vals.p, mega_start.p, M, p->poff.p, p->blk.p, B,
                                                      goff.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
                                                      reinterpret_cast<uint32_t*>(p->sell.p));
       if (p->n_cb > n_mega)
         k_cb_fill<<<grid_for((uint64_t)(p->n_cb - n_mega) * 32, 256), 256, 0, s>>>(
-            g->in.off.p, g->in.tgt.p, old_of.p, p->new_id.p, hot_of_blk.p, p->nrows.p, p->poff.p, p->blk.p, B, n_mega,
-            p->n_cb, deal, goff.p, cur.p, reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p,
-            reinterpret_cast<uint32_t*>(p->sell.p));
+            g->in.off.p, old_of.p, rec.p, p->poff.p, n_mega, p->n_cb, deal, goff.p,
+            reinterpret_cast<uint16_t*>(p->cb_ids.p), p->slice_meta.p, reinterpret_cast<uint32_t*>(p->sell.p));
       GB_CUDA(cudaGetLastError());
       GB_CUDA(cudaStreamSynchronize(s));
     }
@@ -2060,6 +2154,12 @@ gb_status gb_page_rank(const gb_graph* graph, const gb_page_rank_config* config,
   return gb::page_rank_impl(graph, config, nullptr, scores, ran_iterations, error);
 }
 
+// One-shot PageRank of a host CSR.  The 4 bytes per edge of the targets dominate the upload, so they are
+// streamed: offsets first, then the targets in row-aligned chunks on a copy stream, while the graph's own
+// stream sorts the degrees, picks the hot blocks and classifies every chunk as it lands (TargetFeed in
+// build_pr_plan).  Only the fill pass, the sweeps and the copy of the ranks run after the last byte.
+// GB_PR_FEED_CHUNKS (default 16; 0 = upload everything, then build) and GB_PR_FEED_MIN_EDGES (default 2^22)
+// are experiment knobs.
 gb_status gb_page_rank_csr_u32(int device, uint32_t n, const uint32_t* in_off, const uint32_t* in_tgt,
                                const uint32_t* out_off, const gb_page_rank_config* config, float* scores,
                                uint64_t* ran_iterations, double* error) {
@@ -2067,12 +2167,90 @@ gb_status gb_page_rank_csr_u32(int device, uint32_t n, const uint32_t* in_off, c
   GB_REQUIRE(n > 0, "node_count must be > 0");
   GB_REQUIRE(in_off && out_off, "offset arrays are NULL");
   GB_REQUIRE(in_off[n] == out_off[n], "in and out offsets disagree on the edge count");
+  const uint64_t m = in_off[n];
+  uint32_t chunks = gb::env_u32("GB_PR_FEED_CHUNKS", 16);
+  if (m < gb::env_u32("GB_PR_FEED_MIN_EDGES", 1u << 22)) chunks = 0;
+  // the single-warp EXACT mode (small graphs) reads the CSR directly: nothing to overlap
+  if (!config || config->mode == GB_PR_EXACT || (config->mode == GB_PR_AUTO && n <= 16384)) chunks = 0;
   gb_graph* g = nullptr;
   GB_TRY(gb::new_graph(device, GB_KIND_DIRECTED, n, &g));
-  gb_status st = gb::upload_host_csr(g->stream, n, in_off, in_tgt, nullptr, &g->in, "in");
-  if (st == GB_OK) st = gb::upload_host_csr(g->stream, n, out_off, nullptr, nullptr, &g->out, "out");
-  if (st == GB_OK) st = gb::page_rank_impl(g, config, nullptr, scores, ran_iterations, error);
+  if (chunks == 0) {
+    gb_status st = gb::upload_host_csr(g->stream, n, in_off, in_tgt, nullptr, &g->in, "in");
+    if (st == GB_OK) st = gb::upload_host_csr(g->stream, n, out_off, nullptr, nullptr, &g->out, "out");
+    if (st == GB_OK) st = gb::page_rank_impl(g, config, nullptr, scores, ran_iterations, error);
+    gb_graph_free(g);
+    return st;
+  }
+  gb::TargetFeed feed;
+  cudaStream_t copy = nullptr;
+  cudaEvent_t offsets_in = nullptr;
+  gb_status st = [&]() -> gb_status {
+    GB_REQUIRE(in_off[0] == 0 && out_off[0] == 0, "offsets[0] must be 0");
+    GB_REQUIRE(in_tgt != nullptr, "in targets is NULL");
+    GB_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    GB_CUDA(cudaEventCreateWithFlags(&offsets_in, cudaEventDisableTiming));
+    g->in.len = m;
+    g->out.len = m;
+    GB_TRY(g->in.off.alloc((size_t)n + 1));
+    GB_TRY(g->out.off.alloc((size_t)n + 1));
+    GB_TRY(g->in.tgt.alloc(m, 8));
+    GB_CUDA(cudaMemcpyAsync(g->in.off.p, in_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, copy));
+    GB_CUDA(cudaMemcpyAsync(g->out.off.p, out_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, copy));
+    GB_CUDA(cudaEventRecord(offsets_in, copy));
+    GB_CUDA(cudaMemsetAsync(g->in.tgt.p + m, 0, 8 * 4, copy));
+    // chunk boundaries: rows, at about equal edge counts (a monotone in_off is checked on the device below;
+    // a malformed one only makes uneven chunks here, the bounds stay inside [0, m])
+    feed.row_begin.push_back(0);
+    feed.edge_begin.push_back(0);
+    for (uint32_t k = 1; k <= chunks; ++k) {
+      uint32_t v = n;
+      if (k < chunks) {
+        const uint64_t want = m / chunks * k;
+        v = (uint32_t)(std::upper_bound(in_off, in_off + n + 1, (uint32_t)want) - in_off);
+        v = std::min(std::max(v, feed.row_begin.back()), n);
+      }
+      uint64_t e = std::min<uint64_t>(in_off[v], m);
+      e = std::max(e, feed.edge_begin.back());
+      if (k == chunks) e = m;
+      feed.row_begin.push_back(v);
+      feed.edge_begin.push_back(e);
+    }
+    for (uint32_t k = 0; k < chunks; ++k) {
+      const uint64_t e0 = feed.edge_begin[k], e1 = feed.edge_begin[k + 1];
+      if (e1 > e0)
+        GB_CUDA(cudaMemcpyAsync(g->in.tgt.p + e0, in_tgt + e0, (e1 - e0) * 4, cudaMemcpyHostToDevice, copy));
+      cudaEvent_t ev = nullptr;
+      GB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      feed.ready.push_back(ev);
+      GB_CUDA(cudaEventRecord(ev, copy));
+    }
+    // offsets: monotone, checked before anything indexes with them
+    GB_CUDA(cudaStreamWaitEvent(g->stream, offsets_in, 0));
+    gb::DevBuf<unsigned int> bad;
+    GB_TRY(bad.alloc(2));
+    GB_CUDA(cudaMemsetAsync(bad.p, 0, 8, g->stream));
+    gb::k_feed_monotone<<<gb::grid_for(n, 256), 256, 0, g->stream>>>(g->in.off.p, n, bad.p);
+    gb::k_feed_monotone<<<gb::grid_for(n, 256), 256, 0, g->stream>>>(g->out.off.p, n, bad.p + 1);
+    unsigned int nbad[2] = {0, 0};
+    GB_CUDA(cudaMemcpyAsync(nbad, bad.p, 8, cudaMemcpyDeviceToHost, g->stream));
+    GB_CUDA(cudaStreamSynchronize(g->stream));
+    {
+      gb::DevBufStreamScope scope(g->stream);  // do not wait for the copy stream here
+      bad.release();
+    }
+    GB_REQUIRE(nbad[0] == 0, "in offsets are not monotone (%u rows)", nbad[0]);
+    GB_REQUIRE(nbad[1] == 0, "out offsets are not monotone (%u rows)", nbad[1]);
+    g->feed = &feed;
+    gb_status r = gb::page_rank_impl(g, config, nullptr, scores, ran_iterations, error);
+    g->feed = nullptr;
+    return r;
+  }();
+  g->feed = nullptr;
+  if (copy) cudaStreamSynchronize(copy);  // an early error must not free buffers under a running copy
   gb_graph_free(g);
+  for (cudaEvent_t ev : feed.ready) cudaEventDestroy(ev);
+  if (offsets_in) cudaEventDestroy(offsets_in);
+  if (copy) cudaStreamDestroy(copy);
   return st;
 }
 

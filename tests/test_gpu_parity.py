@@ -449,6 +449,41 @@ def test_page_rank_csr_one_shot_matches_resident_twin(gb, rmat16):
         assert it.value == maxit and scores.tobytes() == want.scores().tobytes() and err.value == want.error
 
 
+@pytest.mark.parametrize("chunks,mega", [(1, None), (3, None), (7, "200"), (16, None)])
+def test_page_rank_csr_streamed_upload_matches_resident_twin(gb, rmat16, monkeypatch, chunks, mega):
+    """gb_page_rank_csr_u32 streams the targets in row-aligned chunks and classifies each chunk while the
+    next one is on the bus; the layout it builds is the one the resident twin builds (bit-equal ranks)."""
+    import ctypes as C
+    from graph_b200 import _capi
+    from graph_b200._capi import lib, check
+    src, dst, n, out, inc = rmat16
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    if mega:
+        monkeypatch.setenv("GB_PR_MEGA", mega)
+    g = gb.DiGraph.from_csr(out[0], out[1], inc[0], inc[1])
+    want = g.page_rank(max_iterations=12, tolerance=0.0, mode="jacobi")
+    monkeypatch.setenv("GB_PR_FEED_MIN_EDGES", "0")
+    monkeypatch.setenv("GB_PR_FEED_CHUNKS", str(chunks))
+    cfg = _capi.PageRankConfig(12, 0.0, 0.85, _capi.PR_JACOBI)
+    scores = np.empty(n, np.float32)
+    it, err = C.c_uint64(0), C.c_double(0.0)
+    check(lib.gb_page_rank_csr_u32(0, n, P(inc[0]), P(inc[1]), P(out[0]), C.byref(cfg), P(scores), C.byref(it),
+                                   C.byref(err)))
+    assert it.value == 12 and scores.tobytes() == want.scores().tobytes() and err.value == want.error
+    # the streamed path validates like the resident one
+    bad_tgt = inc[1].copy()
+    bad_tgt[len(bad_tgt) // 2] = n + 5
+    assert lib.gb_page_rank_csr_u32(0, n, P(inc[0]), P(bad_tgt), P(out[0]), C.byref(cfg), P(scores), C.byref(it),
+                                    C.byref(err)) == 1
+    assert b"targets >= node_count" in lib.gb_last_error()
+    bad_off = inc[0].copy()
+    bad_off[5], bad_off[6] = bad_off[6] + 3, bad_off[5]
+    if bad_off[5] > bad_off[6]:
+        assert lib.gb_page_rank_csr_u32(0, n, P(bad_off), P(inc[1]), P(out[0]), C.byref(cfg), P(scores), C.byref(it),
+                                        C.byref(err)) == 1
+        assert b"monotone" in lib.gb_last_error()
+
+
 def test_invalid_host_csr_is_rejected(gb):
     off = np.array([0, 2, 3], np.uint32)
     tgt = np.array([1, 7, 0], np.uint32)          # 7 >= n
