@@ -107,7 +107,7 @@ struct PrPlan {
   DevBuf<uint32_t> tail_slot;   // [n_chunks] staircase slot of the segment cut by the chunk end
   DevBuf<double> side;          // [2 n_chunks] head / tail parts of segments cut by chunk boundaries
   DevBuf<uint32_t> fix_list;    // [n_fix] chunks whose tail segment continues in later chunks
-  DevBuf<uint2> tasks;          // [n_tasks] chunk ranges of one block each, fattest blocks first
+  DevBuf<uint2> tasks;          // [n_tasks] (first chunk, chunk count | block rank << 8), fattest blocks first
   DevBuf<uint32_t> task_ctr;    // [grid_cb] per-range task cursors (reset by the finish kernel)
   DevBuf<float> rem;            // [n_cb] SELL remainder sums of the rows that also have segments
   DevBuf<uint32_t> fin_kb;      // [ceil(n_cb / 32)] blocks of the first row of each 32-row group (finish kernel)
@@ -832,24 +832,64 @@ __device__ __forceinline__ void cb_chunk(const PrArgs& a, const float* xs, uint3
   else cb_chunk_impl<false>(a, xs, c, ch, lane, pad2);
 }
 
+// ---- TMA bulk copy of a source block into shared memory (cp.async.bulk + mbarrier) -----------------
+// One thread asks the copy engine for the block's 192 KB and every thread waits on the mbarrier's phase:
+// no load/store instruction of the CTA is spent on the transfer and it runs at the SM's L2 bandwidth
+// (the LDG.128 -> STS.128 loop it replaces kept one 16 KB wave in flight: 12 round trips per block).
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
 // Persistent CTAs pull TASKS (32 consecutive chunks of one block).  The task list (fattest blocks first)
 // is split into one contiguous RANGE per CTA, each with its own atomic cursor: a CTA first drains its own
 // range — consecutive tasks of one block, so the 192 KB block is loaded once, not once per task — and then
 // steals from the other ranges' cursors.  Self-balancing whatever else shares the SM and however uneven the
 // thin blocks are (a purely static split ran 2.4x slower, one global cursor reloads the block for every
-// task: profiles/r02_sweep_breakdown.txt).
+// task: profiles/r02_sweep_breakdown.txt).  Claiming the next task one task ahead (to hide the atomic's
+// round trip) was measured and dropped: a claimed task cannot be stolen, which costs more at the tail.
 template <int NT>
 __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
   __shared__ uint32_t s_task;
+  __shared__ __align__(8) unsigned long long s_mbar;
   if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t B = a.B;
   const uint32_t pad2 = B | (B << 16);
   const uint32_t R = gridDim.x;  // ranges = CTAs
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+  const uint32_t xs_smem = (uint32_t)__cvta_generic_to_shared(xs);
+  const bool bulk_ok = (reinterpret_cast<uintptr_t>(a.x_cur) & 15u) == 0;  // cp.async.bulk moves 16-byte units
+  uint32_t phase = 0;
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;  // the pad id's zero slot: never overwritten
   uint32_t cur_j = CB_NONE;
   uint32_t r = blockIdx.x;  // range being drained (warp 0 keeps it)
+  __syncthreads();  // mbarrier + zero slot are set up
   for (;;) {
     if (warp == 0) {
       uint32_t t = CB_NONE;
@@ -884,27 +924,30 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
     const uint32_t t = s_task;
     __syncthreads();
     if (t == CB_NONE) break;
-    const uint2 task = a.tasks[t];
-    const uint32_t j = a.chunks[task.x].w & 0xFFFFFFu;
+    const uint2 task = a.tasks[t];  // (first chunk, chunk count | block rank << 8)
+    const uint32_t j = task.y >> 8;
     if (j != cur_j) {
       const uint64_t x0 = (uint64_t)a.blk[j] * B;
-      const float4* src = reinterpret_cast<const float4*>(a.x_cur + x0);
-      for (uint32_t i = threadIdx.x * 4; i < B; i += NT * 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x0 + i + 3 < a.n) {
-          v = __ldg(src + i / 4);
-        } else {
-          if (x0 + i + 0 < a.n) v.x = a.x_cur[x0 + i + 0];
-          if (x0 + i + 1 < a.n) v.y = a.x_cur[x0 + i + 1];
-          if (x0 + i + 2 < a.n) v.z = a.x_cur[x0 + i + 2];
+      const uint32_t cnt = (uint32_t)min((uint64_t)B, (uint64_t)a.n - x0);
+      if (bulk_ok) {
+        const uint32_t bulk = cnt & ~3u;
+        if (threadIdx.x == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the block's old contents were read through the generic proxy
+          mbar_expect_tx(mbar, bulk * 4u);
+          for (uint32_t off = 0; off < bulk; off += 4096u)  // 16 KB pieces
+            bulk_g2s(xs_smem + off * 4u, a.x_cur + x0 + off, min(4096u, bulk - off) * 4u, mbar);
         }
-        *reinterpret_cast<float4*>(xs + i) = v;
+        if (threadIdx.x >= 32 && threadIdx.x - 32 < cnt - bulk) xs[bulk + threadIdx.x - 32] = a.x_cur[x0 + bulk + threadIdx.x - 32];
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      } else {
+        for (uint32_t i = threadIdx.x; i < cnt; i += NT) xs[i] = a.x_cur[x0 + i];
       }
-      if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;
       cur_j = j;
       __syncthreads();
     }
-    for (uint32_t k = task.x + warp; k < task.y; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
+    const uint32_t c_end = task.x + (task.y & 0xFFu);
+    for (uint32_t k = task.x + warp; k < c_end; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
   }
 }
 __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb_body<PR_THREADS>(a); }
@@ -1636,7 +1679,7 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
         const uint32_t nc = (G + h_cgrp[j] - 1) / h_cgrp[j];
         h_cfirst[j + 1] = h_cfirst[j] + nc;
         for (uint32_t c = 0; c < nc; c += CB_TASK_CHUNKS)
-          h_tasks.push_back(make_uint2(h_cfirst[j] + c, h_cfirst[j] + std::min(nc, c + CB_TASK_CHUNKS)));
+          h_tasks.push_back(make_uint2(h_cfirst[j] + c, (std::min(nc, c + CB_TASK_CHUNKS) - c) | (j << 8)));
       }
       p->n_chunks = h_cfirst[p->KB];
       p->n_tasks = (uint32_t)h_tasks.size();

@@ -206,7 +206,9 @@ gb_status gb_page_rank_device(const gb_graph* graph, const gb_page_rank_config* 
 /* One-shot form for a caller that holds the CSR on the host and wants no resident twin: exactly
  * what page_rank reads through its trait bounds (page_rank.rs:61: Graph + DirectedDegrees +
  * DirectedNeighbors) — the in-CSR and the out-degrees (given as out offsets).  Uploads
- * 4m + 8(n+1) bytes instead of the full twin's 8m + 8(n+1). */
+ * 4m + 8(n+1) bytes instead of the full twin's 8m + 8(n+1).  The targets are streamed in row-aligned
+ * chunks and the layout build runs underneath the upload (pass page-locked arrays: from pageable memory
+ * the copies are synchronous and nothing overlaps; the result is the same). */
 gb_status gb_page_rank_csr_u32(int device, uint32_t node_count, const uint32_t* in_offsets,
                                const uint32_t* in_targets, const uint32_t* out_offsets,
                                const gb_page_rank_config* config, float* scores,
