@@ -121,7 +121,7 @@ struct PrPlan {
   unsigned grid_cb = 0, grid_sell = 0, grid_fin = 1;
   uint32_t n_fin_warp = 0;   // rows [0, n_fin_warp) own segments in more than FIN_CTA_BLOCKS blocks
   uint32_t n_fin = 0;        // rows [0, n_fin) are completed by k_pr_finish, [n_fin, n_cb) by k_pr_sell
-  uint32_t few_nrows[SELL_FEW] = {0, 0, 0, 0}, few_poff[SELL_FEW] = {0, 0, 0, 0};
+  uint32_t few_nrows[SELL_FEW] = {}, few_poff[SELL_FEW] = {};
   // dual mode: k_pr_cb and k_pr_sell run at the same time on the same SMs (two streams, 512-thread CTAs)
   bool dual = false;
   cudaStream_t s2 = nullptr;
