@@ -35,7 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 SWEEPS = 20
-PR_KERNEL_VERSION = "r02-cb14"   # bump with every change of the sweep kernels / layout (keys profiles/pr_traffic.json)
+PR_KERNEL_VERSION = "r02-cb16"   # bump with every change of the sweep kernels / layout (keys profiles/pr_traffic.json)
 DAMPING = 0.85
 SEED = 42
 EDGE_FACTOR = 16

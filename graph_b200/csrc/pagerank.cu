@@ -97,6 +97,7 @@ struct PrPlan {
   uint64_t S = 0;               // staircase size = sum of nrows[j]
   uint64_t NG = 0;              // groups in all block streams
   uint32_t chunk_groups = 0, n_chunks = 0, n_tasks = 0, n_fix = 0;
+  uint32_t fix_max_row = 0;     // largest local row that owns a segment cut by a chunk boundary
   DevBuf<uint32_t> blk;         // [KB] source block of hot rank j
   DevBuf<uint32_t> nrows;       // [KB] local rows [0, nrows[j]) have a segment in block j (non-increasing)
   DevBuf<uint32_t> poff;        // [KB+1] staircase offsets
@@ -120,6 +121,8 @@ struct PrPlan {
   DevBuf<float> scores;
   unsigned grid_cb = 0, grid_sell = 0, grid_fin = 1;
   uint32_t n_fin_warp = 0;   // rows [0, n_fin_warp) own segments in more than FIN_CTA_BLOCKS blocks
+  uint32_t fin_u = 4;        // finish: row groups per warp iteration (template argument of k_pr_finish)
+  uint32_t fin_hub_ctas = 0; // finish CTAs that take the hub groups (the others take rows [n_fin_warp, n_fin))
   uint32_t n_fin = 0;        // rows [0, n_fin) are completed by k_pr_finish, [n_fin, n_cb) by k_pr_sell
   uint32_t few_nrows[SELL_FEW] = {}, few_poff[SELL_FEW] = {};
   // dual mode: k_pr_cb and k_pr_sell run at the same time on the same SMs (two streams, 512-thread CTAs)
@@ -619,7 +622,7 @@ __global__ void k_cb_chunks(const uint32_t* __restrict__ goff, const uint32_t* _
                             const uint32_t* __restrict__ nrows, const uint32_t* __restrict__ gbeg,
                             const uint32_t* __restrict__ cfirst, const uint32_t* __restrict__ cgrp, uint32_t KB,
                             uint32_t n_chunks, uint4* __restrict__ chunks, uint32_t* __restrict__ tail_slot,
-                            uint32_t* __restrict__ fix_list, uint32_t* __restrict__ n_fix) {
+                            uint32_t* __restrict__ fix_list, uint32_t* __restrict__ n_fix /* [1] = largest cut row */) {
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = KB;  // block with cfirst[j] <= c < cfirst[j + 1]
     while (hi - lo > 1) {
@@ -642,7 +645,10 @@ __global__ void k_cb_chunks(const uint32_t* __restrict__ goff, const uint32_t* _
     const uint32_t row_before = a.mid ? a.row : a.row - 1;
     chunks[c] = make_uint4(a.pos, b.pos, row_before, j | (fl << 24));
     tail_slot[c] = b.mid ? poff[j] + b.row : CB_NONE;
-    if (b.mid && !(fl & CB_INTERIOR)) fix_list[atomicAdd(n_fix, 1u)] = c;
+    if (b.mid && !(fl & CB_INTERIOR)) {
+      fix_list[atomicAdd(n_fix, 1u)] = c;
+      atomicMax(n_fix + 1, b.row);
+    }
   }
 }
 
@@ -659,9 +665,11 @@ struct PrArgs {
   PrDeal deal;
   uint32_t n_loc, n_cb;
   uint32_t n_fin_warp;  // rows [0, n_fin_warp) own segments in many blocks (finish: one CTA per 32 rows)
+  uint32_t fin_hub_ctas;  // finish: CTAs [0, fin_hub_ctas) take those groups, the rest the other rows
   uint32_t n_fin;       // rows [0, n_fin) are completed by k_pr_finish (rem[] + partials); rows [n_fin, n_cb) own
                         // segments in at most SELL_FEW blocks and are completed by their k_pr_sell lane
   uint32_t few_kb, few_nrows[SELL_FEW], few_poff[SELL_FEW];  // the first blocks' row prefixes / partial offsets
+  uint32_t dbg;         // GB_PR_DEBUG bits (diagnostics): 1 = SELL slices CTA-major, 2 = static chunk->warp map, 4 = no TMA
   uint32_t fix_in_sell; // k_pr_sell adds the parts of cut segments first (sequential mode: no k_pr_fixup launch)
   const uint32_t* fin_kb;  // [ceil(n_cb / 32)] blocks in which the first row of each 32-row group owns a segment
   // column blocks
@@ -874,7 +882,7 @@ template <int NT>
 __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   extern __shared__ __align__(128) float smem[];
   float* xs = smem;  // B entries of x_cur + one zero slot (the pad id)
-  __shared__ uint32_t s_task;
+  __shared__ uint32_t s_task, s_next;
   __shared__ __align__(8) unsigned long long s_mbar;
   if (a.ctrl[0] != 0) return;  // tolerance already met by an earlier sweep of this batch
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -883,7 +891,7 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
   const uint32_t R = gridDim.x;  // ranges = CTAs
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
   const uint32_t xs_smem = (uint32_t)__cvta_generic_to_shared(xs);
-  const bool bulk_ok = (reinterpret_cast<uintptr_t>(a.x_cur) & 15u) == 0;  // cp.async.bulk moves 16-byte units
+  const bool bulk_ok = (reinterpret_cast<uintptr_t>(a.x_cur) & 15u) == 0 && !(a.dbg & 4u);  // cp.async.bulk moves 16-byte units
   uint32_t phase = 0;
   if (threadIdx.x == 0) mbar_init(mbar, 1);
   if (threadIdx.x < 4) xs[B + threadIdx.x] = 0.0f;  // the pad id's zero slot: never overwritten
@@ -922,6 +930,7 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
     }
     __syncthreads();  // also: every warp is done with the previous task's block
     const uint32_t t = s_task;
+    if (threadIdx.x == 0) s_next = NT / 32;  // every warp is past its last claim of the previous task
     __syncthreads();
     if (t == CB_NONE) break;
     const uint2 task = a.tasks[t];  // (first chunk, chunk count | block rank << 8)
@@ -946,8 +955,14 @@ __device__ __forceinline__ void pr_cb_body(const PrArgs& a) {
       cur_j = j;
       __syncthreads();
     }
-    const uint32_t c_end = task.x + (task.y & 0xFFu);
-    for (uint32_t k = task.x + warp; k < c_end; k += NT / 32) cb_chunk(a, xs, k, lane, pad2);
+    // a warp starts with chunk `warp` of the task and claims further ones from the CTA's counter
+    const uint32_t nchunks = task.y & 0xFFu;
+    for (uint32_t k = warp; k < nchunks;) {
+      cb_chunk(a, xs, task.x + k, lane, pad2);
+      uint32_t nx = 0;
+      if (lane == 0) nx = atomicAdd(&s_next, 1u);
+      k = (a.dbg & 2u) ? k + NT / 32 : __shfl_sync(0xFFFFFFFFu, nx, 0);
+    }
   }
 }
 __global__ void __launch_bounds__(PR_THREADS, 1) k_pr_cb(const PrArgs a) { pr_cb_body<PR_THREADS>(a); }
@@ -1003,7 +1018,9 @@ __global__ void __launch_bounds__(PR_SELL_THREADS, 2) k_pr_sell(const PrArgs a) 
   const uint32_t stride = gridDim.x * NW;
   const uint4 pad = make_uint4(~0u, ~0u, ~0u, ~0u);
   const uint32_t P = a.deal.P, pp = a.deal.p;
-  uint32_t sidx = blockIdx.x * NW + warp;
+  // slices are dealt CTA-minor: the widest slices (the first ones) land on different SMs, not on the 16
+  // warps of CTA 0 (an eighth-shard ran with its busiest SM 31 % above the average otherwise)
+  uint32_t sidx = (a.dbg & 1u) ? blockIdx.x * NW + warp : warp * gridDim.x + blockIdx.x;
   // pipeline state: metadata of this and the next slice, first two target groups + row data of this one
   uint2 meta = make_uint2(0, 0), nmeta = meta;
   uint4 ta = pad, tb = pad;
@@ -1108,7 +1125,10 @@ __host__ __device__ __forceinline__ uint32_t fin_blocks_of(const uint32_t* __res
   }
   return lo;
 }
-template <bool PEERS>
+// FIN_U = 32-row groups per warp iteration of the rows that are not hub groups: 2 (and 16 blocks' partials
+// in flight) when every warp has a single iteration to do — the walk is a latency chain, fewer rounds win;
+// 4 (4 blocks in flight) when the grid is capped and the kernel is throughput bound (RMAT-26 on one GPU).
+template <bool PEERS, uint32_t FIN_U>
 __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   constexpr int FIN_WARPS = PR_FIN_THREADS / 32;
   __shared__ double warp_err[FIN_WARPS];
@@ -1119,11 +1139,13 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
   const uint32_t P = a.deal.P, pp = a.deal.p;
   if (blockIdx.x == 0)  // next sweep's column-block task cursors
     for (uint32_t i = threadIdx.x; i < a.n_task_ranges; i += PR_FIN_THREADS) a.task_ctr[i] = 0;
-  const uint32_t gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
   // hub rows (segments in more than FIN_CTA_BLOCKS blocks): one CTA per 32-row group — lane = row,
   // warp w adds blocks w, w + 8, ... (independent coalesced loads), warp 0 adds the 8 sums in order
   __shared__ double part[FIN_WARPS][32];
-  for (uint32_t g = blockIdx.x; g * 32 < a.n_fin_warp; g += gridDim.x) {
+  // fin_hub_ctas != 0: CTAs [0, fin_hub_ctas) take the hub groups, the others the remaining rows
+  const bool split = a.fin_hub_ctas != 0;  // else every CTA does both parts
+  const uint32_t H = split ? a.fin_hub_ctas : gridDim.x, T0 = split ? a.fin_hub_ctas : 0u;
+  for (uint32_t g = blockIdx.x; blockIdx.x < H && g * 32 < a.n_fin_warp; g += H) {
     const uint32_t l = g * 32 + lane;
     const uint32_t kb = __ldg(a.fin_kb + g);  // blocks of the group's first row (it has the most)
     double s = 0.0;
@@ -1141,11 +1163,11 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
     }
     __syncthreads();
   }
-  // all other rows with segments: one lane per row, FIN_U consecutive 32-row groups per warp iteration
-  // (the loads of the groups are independent: the walk is latency bound, not bandwidth bound)
-  constexpr uint32_t FIN_U = 4;
+  // all other rows with segments: one lane per row, FIN_U consecutive 32-row groups per warp iteration,
+  // 16 blocks' partials requested at a time (the walk is latency bound, not bandwidth bound: rounds count)
   const uint32_t tail_groups = (a.n_fin - a.n_fin_warp + 31) / 32;
-  for (uint32_t w = gw * FIN_U; w < tail_groups; w += nw * FIN_U) {
+  const uint32_t tw = (blockIdx.x - T0) * FIN_WARPS + warp, tnw = (gridDim.x - T0) * FIN_WARPS;
+  for (uint32_t w = tw * FIN_U; blockIdx.x >= T0 && w < tail_groups; w += tnw * FIN_U) {
     const uint32_t l0 = a.n_fin_warp + 32 * w;
     const uint32_t kb = __ldg(a.fin_kb + (l0 >> 5));  // blocks of the first row (it has the most)
     uint32_t l[FIN_U], gr[FIN_U], deg[FIN_U];
@@ -1165,7 +1187,7 @@ __global__ void __launch_bounds__(PR_FIN_THREADS) k_pr_finish(const PrArgs a) {
         s[u] = (double)a.rem[l[u]];
       }
     }
-#pragma unroll 4
+#pragma unroll(FIN_U == 2 ? 16 : 4)
     for (uint32_t j = 0; j < kb; ++j) {
       const uint32_t nr = __ldg(a.nrows + j);
       const float* __restrict__ pj = a.partial + __ldg(a.poff + j);
@@ -1668,7 +1690,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       // >= 64 chunks (down to one 64-group step each) so that all warps share it — a lone warp runs at
       // its dependency latency, ~10x below the SM's throughput
       uint32_t C = env_u32("GB_PR_CHUNK", 0);
-      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 8 * CB_TASK_CHUNKS), 512), 2048);
+      const uint32_t T = std::min<uint32_t>(std::max<uint32_t>(env_u32("GB_PR_TASK_CHUNKS", CB_TASK_CHUNKS), 32u), 128u);
+      if (!C) C = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p->NG / ((uint64_t)dev_sms * 8 * T), 16384 / T), 65536 / T);
       C = std::max<uint32_t>(32u, (C + 31) / 32 * 32);
       p->chunk_groups = C;
       std::vector<uint32_t> h_cfirst(p->KB + 1, 0), h_cgrp(p->KB, C);
@@ -1678,8 +1701,8 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
         h_cgrp[j] = std::min<uint32_t>(C, std::max<uint32_t>(std::min<uint32_t>(64u, C), (G / 64 + 63) / 64 * 64));
         const uint32_t nc = (G + h_cgrp[j] - 1) / h_cgrp[j];
         h_cfirst[j + 1] = h_cfirst[j] + nc;
-        for (uint32_t c = 0; c < nc; c += CB_TASK_CHUNKS)
-          h_tasks.push_back(make_uint2(h_cfirst[j] + c, (std::min(nc, c + CB_TASK_CHUNKS) - c) | (j << 8)));
+        for (uint32_t c = 0; c < nc; c += T)
+          h_tasks.push_back(make_uint2(h_cfirst[j] + c, (std::min(nc, c + T) - c) | (j << 8)));
       }
       p->n_chunks = h_cfirst[p->KB];
       p->n_tasks = (uint32_t)h_tasks.size();
@@ -1699,8 +1722,11 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
                                                            p->KB, p->n_chunks, p->chunks.p, p->tail_slot.p,
                                                            p->fix_list.p, d_nfix);
       GB_CUDA(cudaGetLastError());
-      GB_CUDA(cudaMemcpyAsync(&p->n_fix, d_nfix, 4, cudaMemcpyDeviceToHost, s));
+      uint32_t h_fix[2] = {0, 0};
+      GB_CUDA(cudaMemcpyAsync(h_fix, d_nfix, 8, cudaMemcpyDeviceToHost, s));
       GB_CUDA(cudaStreamSynchronize(s));
+      p->n_fix = h_fix[0];
+      p->fix_max_row = h_fix[1];
     } else {
       GB_TRY(p->chunks.alloc(1));
       GB_TRY(p->tail_slot.alloc(1));
@@ -1741,9 +1767,22 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
       p->few_poff[j] = h_poff[j];
     }
     p->n_fin_warp = p->KB > FIN_CTA_BLOCKS ? std::min<uint32_t>(p->n_fin, (h_nrows[FIN_CTA_BLOCKS] + 31) / 32 * 32) : 0;
-    const uint64_t fin_tasks = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_fin - p->n_fin_warp + 127) / 128;
+    const uint64_t fin_warps2 = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_fin - p->n_fin_warp + 63) / 64;
+    const uint64_t fin_warps4 = (uint64_t)p->n_fin_warp / 32 * (PR_FIN_THREADS / 32) + (p->n_fin - p->n_fin_warp + 127) / 128;
+    p->fin_u = (fin_warps2 + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32) <= (uint64_t)dev_sms * 8 ? 2 : 4;
+    const uint64_t fin_tasks = p->fin_u == 2 ? fin_warps2 : fin_warps4;
     const uint64_t want_fin = (fin_tasks + PR_FIN_THREADS / 32 - 1) / (PR_FIN_THREADS / 32);
     p->grid_fin = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want_fin, (uint64_t)dev_sms * 8));
+    // Role split of the finish CTAs: when every CTA has at most one pass of each kind to do (the grid is not
+    // capped) and the hub chain is long (hundreds of blocks per row), CTAs [0, hub groups) take one hub
+    // group each and the others the remaining rows — the two latency chains then run side by side instead
+    // of one after the other in every CTA.  Measured (profiles/r02_sweep_breakdown.txt): -20 % on an
+    // eighth-shard of RMAT-26; no gain when the grid is capped (RMAT-26 on one GPU) or the hub chain is
+    // short (RMAT-22), where every CTA keeps doing both parts.
+    p->fin_hub_ctas = 0;
+    if (want_fin <= (uint64_t)dev_sms * 8 && p->KB > 4 * FIN_CTA_BLOCKS && p->n_fin_warp && p->n_fin > p->n_fin_warp &&
+        p->grid_fin > p->n_fin_warp / 32)
+      p->fin_hub_ctas = p->n_fin_warp / 32;
     const size_t nerr = (size_t)p->grid_sell + p->grid_fin;
     GB_TRY(p->block_err.alloc(nerr));
     GB_CUDA(cudaMemsetAsync(p->block_err.p, 0, nerr * sizeof(double), s));
@@ -1761,6 +1800,12 @@ static gb_status build_pr_plan(const gb_graph* g, PrDeal deal, PrPlan** out_plan
   return GB_OK;
 }
 
+// The parts of segments cut by chunk boundaries are added by the first warps of k_pr_sell when every such
+// row is completed later, by k_pr_finish (rows below n_fin).  A row that its k_pr_sell lane completes itself
+// (few hot blocks: small graphs) needs the sum BEFORE that kernel: k_pr_fixup runs in between.
+static bool fix_in_sell(const PrPlan* p) {
+  return !p->dual && p->n_fix && p->grid_sell && p->fix_max_row < p->n_fin;
+}
 static PrArgs make_args(const PrPlan* p, float base, float damping, double tolerance) {
   PrArgs a{};
   a.outdeg = p->outdeg.p;
@@ -1769,13 +1814,15 @@ static PrArgs make_args(const PrPlan* p, float base, float damping, double toler
   a.n_loc = p->n_loc;
   a.n_cb = p->n_cb;
   a.n_fin_warp = p->n_fin_warp;
+  a.fin_hub_ctas = p->fin_hub_ctas;
   a.n_fin = p->n_fin;
   a.few_kb = std::min<uint32_t>(p->KB, SELL_FEW);
   for (uint32_t j = 0; j < SELL_FEW; ++j) {
     a.few_nrows[j] = p->few_nrows[j];
     a.few_poff[j] = p->few_poff[j];
   }
-  a.fix_in_sell = (!p->dual && p->n_fix && p->grid_sell) ? 1u : 0u;
+  a.fix_in_sell = fix_in_sell(p) ? 1u : 0u;
+  a.dbg = env_u32("GB_PR_DEBUG", 0);
   a.B = p->B;
   a.KB = p->KB;
   a.blk = p->blk.p;
@@ -1848,13 +1895,15 @@ static gb_status launch_sweep(const PrPlan* p, const PrArgs& a, cudaStream_t s, 
       *launches += 1;
     }
     if (ev) GB_CUDA(cudaEventRecord(ev[3], s));
-    k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+    if (p->fin_u == 2) k_pr_finish<PEERS, 2><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+    else k_pr_finish<PEERS, 4><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
     if (ev) GB_CUDA(cudaEventRecord(ev[4], s));
     *launches += 1;
     GB_CUDA(cudaGetLastError());
     return GB_OK;
   }
-  k_pr_finish<PEERS><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+  if (p->fin_u == 2) k_pr_finish<PEERS, 2><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
+  else k_pr_finish<PEERS, 4><<<p->grid_fin, PR_FIN_THREADS, 0, s>>>(a);
   *launches += 1;
   GB_CUDA(cudaGetLastError());
   return GB_OK;
@@ -2165,7 +2214,7 @@ gb_status gb_pr_shard_info(const gb_pr_shard* shard, gb_pr_shard_stats* stats) {
   stats->cut_segments = p->n_fix;
   stats->chunk_groups = p->chunk_groups;
   stats->launches_per_sweep = 1 + (p->grid_cb ? 1 : 0) + (p->grid_sell ? 1 : 0) +
-                              (p->grid_cb && p->n_fix && (p->dual || !p->grid_sell) ? 1 : 0);
+                              (p->grid_cb && p->n_fix && !gb::fix_in_sell(p) ? 1 : 0);
   stats->device_bytes = p->bytes();
   return GB_OK;
 }

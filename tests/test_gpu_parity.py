@@ -177,6 +177,17 @@ def test_page_rank_exact_mode_equals_single_thread_reference(gb, scale):
         assert pr.error == err
 
 
+@pytest.mark.parametrize("scale", [16, 18, 20])
+def test_page_rank_repeated_runs_are_bit_equal(gb, scale):
+    """Regression: with <= 4 hot blocks (scale 18: exactly 4) the hub rows are completed by their k_pr_sell
+    lane, so the parts of their cut segments must be summed BEFORE that kernel (k_pr_fixup), not by its
+    first warps — a race that showed up as run-to-run differences in the last bits."""
+    g = gb.DiGraph.rmat(scale, seed=7, layout=gb.Layout.Sorted)
+    first = g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores().tobytes()
+    for _ in range(25):
+        assert g.page_rank(max_iterations=20, tolerance=0.0, mode="jacobi").scores().tobytes() == first
+
+
 @pytest.mark.parametrize("scale,seed", [(8, 42), (13, 42), (16, 42), (18, 7)])
 def test_page_rank_jacobi_vs_oracle(gb, scale, seed):
     src, dst = oracle.rmat_edges(scale, seed=seed)
