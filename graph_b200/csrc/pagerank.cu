@@ -16,8 +16,8 @@
 // BLOCKED: vertices are renumbered by in-degree descending, then out-degree descending (hot sources
 // first); the source vector is cut into blocks of B entries that fit in shared memory, and every
 // (row, block) pair that is expected to hold at least tau edges gets a SEGMENT of 16-bit block-local
-// source ids in that block's stream.  A persistent CTA loads a block into shared memory with 128-bit
-// loads, then its warps stream the segments (coalesced 128-bit loads, 8 ids per lane), gather from
+// source ids in that block's stream.  A persistent CTA brings a block into shared memory with TMA bulk
+// copies (cp.async.bulk + mbarrier), then its warps stream the segments (coalesced 128-bit loads, 8 ids per lane), gather from
 // shared memory, and reduce lanes that belong to the same row with a segmented warp scan; one f32
 // partial per (row, block) pair goes back to HBM.  Edges of pairs below the threshold (and all edges
 // of short rows) stay in a SELL-32 layout with 32-bit ids: one lane per row, gathers through L1/L2
