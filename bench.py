@@ -428,7 +428,7 @@ def run_multi(args):
         gh = gb.DiGraph.for_page_rank(in_off, in_tgt, out_off)
         spr.rebind(gh)
         spr.run(SWEEPS, DAMPING)
-        host = spr.scores_host()
+        host = spr.scores_host(reuse=True)   # page-locked, like the N = 1 path's result buffer
         del gh
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
