@@ -187,3 +187,36 @@ def test_errors_keep_their_classes(client):
         w.done_writing()
         r.read()
         w.close()
+
+
+def test_device_engine_calls_bind_to_the_package_api():
+    """B200Engine is exercised on the GPU only; here its calls are bound against the real signatures of
+    graph_b200 (the library loads without a device), so that a renamed keyword cannot hide until then."""
+    import inspect
+    import graph_b200 as gb
+    from graph_b200.flight import B200Engine, LAYOUTS
+    eng = B200Engine()
+    for name in LAYOUTS:
+        assert eng._layout(name) is getattr(gb.Layout, name)
+    lay, fmt = gb.Layout.Sorted, gb.FileFormat.EdgeList
+    assert gb.FileFormat.Graph500 is not gb.FileFormat.EdgeList
+    bind = lambda fn, *a, **k: inspect.signature(fn).bind(*a, **k)
+    bind(gb.DiGraph.load, "p", lay, fmt)
+    bind(gb.DiGraph.load_weighted, "p", lay)
+    bind(gb.Graph.load, "p", lay, fmt)
+    bind(gb.DiGraph.from_numpy, np.zeros((1, 2), np.uint32), lay)
+    bind(gb.Graph.from_numpy, np.zeros((1, 2), np.uint32), lay)
+    bind(gb._read_edge_list, "p", with_values=True)
+    bind(gb.DiGraph.page_rank, None, max_iterations=1, tolerance=0.0, damping_factor=0.85)
+    bind(gb.DiGraph.wcc, None, chunk_size=1, neighbor_rounds=1, sampling_size=1)
+    bind(gb.DiGraph.delta_stepping, None, start_node=0, delta=1.0)
+    bind(gb.DiGraph.to_undirected, None, lay)
+    bind(gb.Graph.global_triangle_count, None)
+    bind(gb.Graph.make_degree_ordered, None)
+    pr = gb.PageRankResult(np.zeros(2, np.float32), 3, 0.5, 1)
+    assert pr.scores().dtype == np.float32 and pr.ran_iterations == 3 and pr.error == 0.5
+    assert gb.WccResult(np.zeros(2, np.uint32), 1).components().dtype == np.uint32
+    assert gb.SsspResult(np.zeros(2, np.float32), 1).distances().dtype == np.float32
+    assert gb.TriangleCountResult(7, 1).triangles == 7
+    # read-only result arrays (the package marks them so) convert to Arrow without a copy error
+    assert pa.array(pr.scores(), pa.float32()).to_pylist() == [0.0, 0.0]
